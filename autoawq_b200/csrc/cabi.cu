@@ -1,0 +1,156 @@
+// extern "C" surface of libb200awq.so (include/b200awq.h): argument validation, path selection,
+// error translation.  Kernels live in dequant.cu / gemv.cu / gemm_tc.cu / aux.cu.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/b200awq.h"
+#include "kernels.h"
+
+namespace b200awq {
+
+static std::atomic<int> g_knobs[8] = {{0}, {0}, {8}, {0}, {0}, {0}, {0}, {0}};
+int knob(int key) { return (key >= 0 && key < 8) ? g_knobs[key].load(std::memory_order_relaxed) : 0; }
+
+static thread_local char g_cuda_err[256] = "";
+
+static int fold(cudaError_t e) {
+  if (e == cudaSuccess) return B200AWQ_OK;
+  std::snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+  (void)cudaGetLastError();  // clear sticky launch-config errors
+  if (e == cudaErrorNotSupported) return B200AWQ_EUNSUPPORTED;
+  if (e == cudaErrorMisalignedAddress || e == cudaErrorInvalidValue) return B200AWQ_EINVAL;
+  return B200AWQ_ECUDA;
+}
+
+static bool shape_ok(int M, int K, int N, int G) {
+  return M >= 0 && K > 0 && N > 0 && G > 0 && (K % G) == 0 && (N % 8) == 0;
+}
+
+struct Ws {
+  int* tickets;
+  float* acc;
+};
+static bool carve(void* ws, size_t bytes, int M, int N, Ws* out) {
+  out->tickets = nullptr;
+  out->acc = nullptr;
+  if (ws == nullptr) return false;
+  const int rows = M < kMaxSplitM ? M : kMaxSplitM;
+  const size_t need = kTicketBytes + (size_t)rows * N * sizeof(float);
+  if (bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return false;
+  out->tickets = reinterpret_cast<int*>(ws);
+  out->acc = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kTicketBytes);
+  return true;
+}
+
+}  // namespace b200awq
+
+using namespace b200awq;
+
+extern "C" {
+
+int b200awq_abi_version(void) { return B200AWQ_ABI_VERSION; }
+
+const char* b200awq_error_string(int code) {
+  switch (code) {
+    case B200AWQ_OK: return "ok";
+    case B200AWQ_EINVAL: return "invalid argument (shape, null or misaligned pointer)";
+    case B200AWQ_EUNSUPPORTED: return "shape not supported by this path";
+    case B200AWQ_EWORKSPACE: return "workspace missing or too small (see b200awq_workspace_bytes)";
+    case B200AWQ_ECUDA: return "CUDA error (see b200awq_last_cuda_error)";
+    case B200AWQ_EARCH: return "device is not sm_100";
+    default: return "unknown error code";
+  }
+}
+
+const char* b200awq_last_cuda_error(void) { return g_cuda_err; }
+
+size_t b200awq_workspace_bytes(int M, int K, int N) {
+  (void)K;
+  if (M < 0 || N <= 0) return 0;
+  const int rows = M < kMaxSplitM ? M : kMaxSplitM;
+  return kTicketBytes + (size_t)rows * N * sizeof(float);
+}
+
+int b200awq_set_knob(int key, int value) {
+  if (key < 0 || key >= 8) return B200AWQ_EINVAL;
+  g_knobs[key].store(value, std::memory_order_relaxed);
+  return B200AWQ_OK;
+}
+int b200awq_get_knob(int key) { return knob(key); }
+
+int b200awq_dequantize_gemm(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out_f16, int K,
+                            int N, int group_size, b200awq_stream_t stream) {
+  const int G = group_size <= 0 ? K : group_size;
+  if (!qweight || !scales || !qzeros || !out_f16 || !shape_ok(1, K, N, G)) return B200AWQ_EINVAL;
+  return fold(dequantize_gemm(qweight, scales, qzeros, out_f16, K, N, G, static_cast<cudaStream_t>(stream)));
+}
+
+int b200awq_gemm_forward(const void* x, int64_t ldx, const int32_t* qweight, const void* scales,
+                         const int32_t* qzeros, const void* bias, void* y, int M, int K, int N, int group_size,
+                         void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
+  const int G = group_size <= 0 ? K : group_size;
+  if (!shape_ok(M, K, N, G) || ldx < K) return B200AWQ_EINVAL;
+  if (M == 0) return B200AWQ_OK;
+  if (!x || !qweight || !scales || !qzeros || !y) return B200AWQ_EINVAL;
+  GemmArgs a{x, ldx, qweight, scales, qzeros, bias, y, M, K, N, G};
+  Ws ws;
+  const bool have_ws = carve(workspace, workspace_bytes, M, N, &ws);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M <= knob(2)) {
+    if (!have_ws) return B200AWQ_EWORKSPACE;  // the GEMV splits K across CTAs
+    if ((N + 7) / 8 > 4096 * 8) return B200AWQ_EUNSUPPORTED;
+    return fold(gemv_gemm_layout(a, ws.acc, ws.tickets, st));
+  }
+  return fold(gemm_tc(a, 0, ws.acc, ws.tickets, st));
+}
+
+int b200awq_gemv_forward(const void* x, int64_t ldx, const int32_t* qweight, const void* scales,
+                         const int32_t* qzeros, const void* bias, void* y, int M, int K, int N, int group_size,
+                         void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
+  const int G = group_size <= 0 ? K : group_size;
+  if (!shape_ok(M, K, N, G) || ldx < K || (K % 32) != 0) return B200AWQ_EINVAL;
+  if (G != 32 && G != 64 && G < 128) return B200AWQ_EUNSUPPORTED;  // calculate_zeros_width's domain
+  if (M == 0) return B200AWQ_OK;
+  if (!x || !qweight || !scales || !qzeros || !y) return B200AWQ_EINVAL;
+  GemmArgs a{x, ldx, qweight, scales, qzeros, bias, y, M, K, N, G};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M <= knob(2)) return fold(gemv_gemv_layout(a, st));
+  Ws ws;
+  carve(workspace, workspace_bytes, M, N, &ws);
+  return fold(gemm_tc(a, 1, ws.acc, ws.tickets, st));
+}
+
+int b200awq_fast_forward(const void* x, int64_t ldx, const int16_t* qweight, const void* scales,
+                         const void* scaled_zeros, const void* bias, void* y, int M, int K, int N, int group_size,
+                         void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
+  const int G = group_size <= 0 ? K : group_size;
+  if (!shape_ok(M, K, N, G) || ldx < K || (K % 64) != 0 || (G % 32) != 0) return B200AWQ_EINVAL;
+  if (M == 0) return B200AWQ_OK;
+  if (!x || !qweight || !scales || !scaled_zeros || !y) return B200AWQ_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M <= knob(2)) {
+    FastArgs f{x, ldx, qweight, scales, scaled_zeros, bias, y, M, K, N, G};
+    return fold(gemv_fast_layout(f, st));
+  }
+  GemmArgs a{x, ldx, reinterpret_cast<const int32_t*>(qweight), scales,
+             reinterpret_cast<const int32_t*>(scaled_zeros), bias, y, M, K, N, G};
+  Ws ws;
+  carve(workspace, workspace_bytes, M, N, &ws);
+  return fold(gemm_tc(a, 2, ws.acc, ws.tickets, st));
+}
+
+int b200awq_rmsnorm(const void* x, const void* weight, void* out, int rows, int hidden, float eps,
+                    b200awq_stream_t stream) {
+  if (!x || !weight || !out || rows < 0 || hidden <= 0) return B200AWQ_EINVAL;
+  if (rows == 0) return B200AWQ_OK;
+  return fold(rmsnorm(x, weight, out, rows, hidden, eps, static_cast<cudaStream_t>(stream)));
+}
+
+int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200awq_stream_t stream) {
+  if (!gate_up || !out || rows < 0 || d <= 0) return B200AWQ_EINVAL;
+  if (rows == 0) return B200AWQ_OK;
+  return fold(silu_and_mul(gate_up, out, rows, d, static_cast<cudaStream_t>(stream)));
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// Internal launcher interface between the C-ABI layer (cabi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200awq {
+
+struct GemmArgs {
+  const void* x;        // [M, ldx] fp16
+  int64_t ldx;
+  const int32_t* qweight;
+  const void* scales;
+  const int32_t* qzeros;
+  const void* bias;     // [N] fp16 or nullptr
+  void* y;              // [M, N] fp16
+  int M, K, N, G;
+};
+
+struct FastArgs {
+  const void* x;
+  int64_t ldx;
+  const int16_t* qweight;  // [N/4, K]
+  const void* scales;      // [8 zw, N]
+  const void* szeros;      // [8 zw, N] = -z*s
+  const void* bias;
+  void* y;
+  int M, K, N, G;
+};
+
+// workspace carve-up (see b200awq_workspace_bytes): tickets first, fp32 accumulators after
+constexpr size_t kTicketBytes = 16384;  // 4096 int tickets
+constexpr int kMaxSplitM = 64;          // rows of fp32 scratch kept for split-K
+
+// knobs (cabi.cu)
+int knob(int key);
+
+cudaError_t dequantize_gemm(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out, int K,
+                            int N, int G, cudaStream_t st);
+
+cudaError_t gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st);
+cudaError_t gemv_gemv_layout(const GemmArgs& a, cudaStream_t st);
+cudaError_t gemv_fast_layout(const FastArgs& a, cudaStream_t st);
+
+// tensor-core path; layout: 0 = GEMM, 1 = GEMV, 2 = FAST (qweight/qzeros reinterpretations documented in gemm_tc.cu)
+cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, cudaStream_t st);
+
+cudaError_t rmsnorm(const void* x, const void* w, void* out, int rows, int hidden, float eps, cudaStream_t st);
+cudaError_t silu_and_mul(const void* gate_up, void* out, int rows, int d, cudaStream_t st);
+
+}  // namespace b200awq

@@ -1,0 +1,212 @@
+"""Torch-facing operator layer: the functions the reference imports from `awq_ext` / `awq_v2_ext`
+(call sites: awq/modules/linear/gemm.py:51-58, gemv.py:168-180, gemv_fast.py:192-205,
+awq/modules/fused/norm.py:33-36, moe.py:76), implemented on the C ABI of libb200awq.so.
+
+torch is plumbing only: device memory (caching allocator), the current stream, dtype/shape checks.
+Every function launches on torch's current stream, never synchronises and is CUDA-graph capturable
+once the per-(device, stream) workspace exists (first call on that stream allocates it).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+from ._cabi import B200AwqError, check, lib
+
+__all__ = [
+    "gemm_forward_cuda", "dequantize_weights_cuda", "gemv_forward_cuda", "gemmv2_forward_cuda",
+    "gemv_forward_cuda_decode", "gemm_forward_cuda_prefill", "layernorm_forward_cuda", "silu_and_mul",
+    "linear_forward", "set_knob", "get_knob", "B200AwqError",
+]
+
+_WS: dict = {}
+_WS_MIN = 16 << 20
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise B200AwqError("b200awq: tensors must live on a CUDA device (there is no CPU path)")
+
+
+def _workspace(dev: torch.device, stream_ptr: int, need: int) -> torch.Tensor:
+    key = (dev.index, stream_ptr)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, _WS_MIN), dtype=torch.uint8, device=dev)
+        _WS[key] = ws
+    return ws
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class _DeviceGuard:
+    """Launch on the tensor's device even when it is not the current one (accelerate places layers
+    on several GPUs; the reference's Triton path does the same guard, awq/modules/triton/gemm.py:23-27)."""
+
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, dev: torch.device):
+        self.dev, self.prev = dev.index, None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if cur != self.dev:
+            self.prev = cur
+            torch.cuda.set_device(self.dev)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def _x2d(x: torch.Tensor, K: int) -> torch.Tensor:
+    if x.dtype != torch.float16:
+        raise B200AwqError(f"b200awq: activations must be float16, got {x.dtype}")
+    if x.shape[-1] != K:
+        raise B200AwqError(f"b200awq: activation feature dim {x.shape[-1]} != in_features {K}")
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < K):
+        x2 = x2.contiguous()
+    return x2
+
+
+def _check_w(t: torch.Tensor, dtype, name: str):
+    if t.dtype != dtype or not t.is_contiguous():
+        raise B200AwqError(f"b200awq: {name} must be contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+
+
+def linear_forward(layout: str, x, qweight, scales, qzeros, group_size: int, bias=None) -> torch.Tensor:
+    """Y = X . deq(W) (+ bias) for layout in {"gemm", "gemv", "fast"}; returns [M, N] fp16."""
+    _require_cuda(x, qweight, scales, qzeros, bias)
+    if layout == "gemm":
+        K, N = qweight.shape[0], qweight.shape[1] * 8
+        fn, wdt = lib.b200awq_gemm_forward, torch.int32
+    elif layout == "gemv":
+        N, K = qweight.shape[0], qweight.shape[1] * 8
+        fn, wdt = lib.b200awq_gemv_forward, torch.int32
+    elif layout == "fast":
+        N, K = qweight.shape[0] * 4, qweight.shape[1]
+        fn, wdt = lib.b200awq_fast_forward, torch.int16
+    else:
+        raise ValueError(layout)
+    _check_w(qweight, wdt, "qweight")
+    _check_w(scales, torch.float16, "scales")
+    _check_w(qzeros, torch.float16 if layout == "fast" else torch.int32, "qzeros")
+    x2 = _x2d(x, K)
+    M = x2.shape[0]
+    dev = x2.device
+    y = torch.empty((M, N), dtype=torch.float16, device=dev)
+    if M == 0:
+        return y
+    G = K if group_size in (-1, 0) else int(group_size)
+    with _DeviceGuard(dev):
+        st = _stream(dev)
+        need = lib.b200awq_workspace_bytes(M, K, N)
+        ws = _workspace(dev, st, need)
+        ldx = x2.stride(0) if M > 1 else K
+        code = fn(x2.data_ptr(), ldx, qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(),
+                  bias.data_ptr() if bias is not None else None, y.data_ptr(), M, K, N, G,
+                  ws.data_ptr(), ws.numel(), st)
+    check(code, f"b200awq_{layout}_forward(M={M}, K={K}, N={N}, G={G})")
+    return y
+
+
+# ----------------------------------------------------------------------------- awq_ext surface
+def gemm_forward_cuda(x, qweight, scales, qzeros, split_k_iters=8):
+    """awq_ext.gemm_forward_cuda (gemm.py:56-58): x [M, K] f16, GEMM layout -> [M, N] f16.
+    `split_k_iters` is a legacy hint of the reference kernels; accepted and ignored."""
+    K = qweight.shape[0]
+    G = K // scales.shape[0]
+    out = linear_forward("gemm", x, qweight, scales, qzeros, G)
+    return out.reshape(x.shape[:-1] + (out.shape[-1],))
+
+
+def dequantize_weights_cuda(qweight, scales, qzeros, split_k_iters=0, thx=0, thy=0, dbg=False):
+    """awq_ext.dequantize_weights_cuda (gemm.py:51-53, tests/test_dequantization.py:41-49) -> [K, N] f16."""
+    _require_cuda(qweight, scales, qzeros)
+    _check_w(qweight, torch.int32, "qweight")
+    _check_w(scales, torch.float16, "scales")
+    _check_w(qzeros, torch.int32, "qzeros")
+    K, N = qweight.shape[0], qweight.shape[1] * 8
+    G = K // scales.shape[0]
+    dev = qweight.device
+    out = torch.empty((K, N), dtype=torch.float16, device=dev)
+    with _DeviceGuard(dev):
+        code = lib.b200awq_dequantize_gemm(qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(), out.data_ptr(),
+                                           K, N, G, _stream(dev))
+    check(code, f"b200awq_dequantize_gemm(K={K}, N={N}, G={G})")
+    return out
+
+
+def gemv_forward_cuda(x, qweight, scales, qzeros, group_size):
+    """awq_ext.gemv_forward_cuda (gemv.py:177-180): GEMV layout, M <= 8."""
+    out = linear_forward("gemv", x, qweight, scales, qzeros, group_size)
+    return out.reshape(x.shape[:-1] + (out.shape[-1],))
+
+
+def gemmv2_forward_cuda(x, qweight, scales, qzeros, group_size, split_k_iters=8):
+    """awq_ext.gemmv2_forward_cuda (gemv.py:168-176): GEMV layout, M > 8."""
+    out = linear_forward("gemv", x, qweight, scales, qzeros, group_size)
+    return out.reshape(x.shape[:-1] + (out.shape[-1],))
+
+
+def layernorm_forward_cuda(x, weight, out, eps):
+    """awq_ext.layernorm_forward_cuda (fused/norm.py:33-36): RMSNorm written into `out`."""
+    _require_cuda(x, weight, out)
+    if x.dtype != torch.float16 or weight.dtype != torch.float16 or out.dtype != torch.float16:
+        raise B200AwqError("b200awq: rmsnorm expects float16 tensors")
+    hidden = x.shape[-1]
+    xc = x if x.is_contiguous() else x.contiguous()
+    if not out.is_contiguous():
+        raise B200AwqError("b200awq: rmsnorm output must be contiguous")
+    rows = xc.numel() // hidden
+    with _DeviceGuard(x.device):
+        code = lib.b200awq_rmsnorm(xc.data_ptr(), weight.data_ptr(), out.data_ptr(), rows, hidden, float(eps),
+                                   _stream(x.device))
+    check(code, "b200awq_rmsnorm")
+
+
+def silu_and_mul(out, gate_up):
+    """awq_ext.silu_and_mul (fused/moe.py:76): out[.., d] = silu(gate_up[.., :d]) * gate_up[.., d:]."""
+    _require_cuda(out, gate_up)
+    d = out.shape[-1]
+    if gate_up.shape[-1] != 2 * d or not gate_up.is_contiguous() or not out.is_contiguous():
+        raise B200AwqError("b200awq: silu_and_mul expects contiguous [.., 2d] -> [.., d]")
+    rows = out.numel() // d
+    with _DeviceGuard(out.device):
+        code = lib.b200awq_silu_and_mul(gate_up.data_ptr(), out.data_ptr(), rows, d, _stream(out.device))
+    check(code, "b200awq_silu_and_mul")
+
+
+# ---------------------------------------------------------------------------- awq_v2_ext surface
+def _fast_group_size(K: int, rows: int) -> int:
+    from .packing import calculate_zeros_width
+
+    for g in (128, 64, 32):
+        if K % g == 0 and calculate_zeros_width(K, g) * 8 == rows:
+            return g
+    raise B200AwqError(f"b200awq: cannot infer group size from scales rows={rows}, K={K}")
+
+
+def gemv_forward_cuda_decode(x, qweight, scales, szeros, m, n, k, group_size):
+    """awq_v2_ext.gemv_forward_cuda_decode (gemv_fast.py:192-201): x [B, 1, K] -> [B, 1, N]."""
+    out = linear_forward("fast", x, qweight, scales, szeros, group_size)
+    return out.reshape(x.shape[:-1] + (out.shape[-1],))
+
+
+def gemm_forward_cuda_prefill(x, qweight, scales, szeros):
+    """awq_v2_ext.gemm_forward_cuda_prefill (gemv_fast.py:203-205): x [B, S, K] -> [B, S, N]."""
+    K = qweight.shape[1]
+    out = linear_forward("fast", x, qweight, scales, szeros, _fast_group_size(K, scales.shape[0]))
+    return out.reshape(x.shape[:-1] + (out.shape[-1],))
+
+
+def set_knob(key: int, value: int) -> None:
+    check(lib.b200awq_set_knob(key, value), "b200awq_set_knob")
+
+
+def get_knob(key: int) -> int:
+    return lib.b200awq_get_knob(key)

@@ -1,0 +1,99 @@
+/* b200awq.h - C ABI of the B200 (sm_100a) AWQ W4A16 linear path.
+ *
+ * This is the drop-in boundary: a plain C shared library (libb200awq.so) whose entry points are what a
+ * replacement for the reference's `awq_ext` / `awq_v2_ext` pybind modules binds.  No torch types: device
+ * pointers, sizes, a CUDA stream.  All pointers are DEVICE pointers unless stated; fp16 tensors are passed
+ * as `const void*` (IEEE binary16).  Every function launches asynchronously on `stream`, never
+ * synchronises, never allocates (CUDA-graph capturable) and returns 0 on success or a B200AWQ_E* code
+ * (b200awq_error_string() explains it; `cudaGetLastError` state is folded into B200AWQ_ECUDA).
+ *
+ * Reference interface each entry point replaces (file:line under casper-hansen/AutoAWQ @ 88e4c76):
+ *   b200awq_dequantize_gemm ...... awq_ext.dequantize_weights_cuda  awq/modules/linear/gemm.py:51-53,100-102
+ *                                                                   tests/test_dequantization.py:40-49
+ *   b200awq_gemm_forward ......... awq_ext.gemm_forward_cuda        awq/modules/linear/gemm.py:56-58
+ *                                   (+ the dequant+matmul branch)   awq/modules/linear/gemm.py:50-54
+ *   b200awq_gemv_forward ......... awq_ext.gemv_forward_cuda        awq/modules/linear/gemv.py:177-180
+ *                                   awq_ext.gemmv2_forward_cuda     awq/modules/linear/gemv.py:168-176
+ *   b200awq_fast_forward ......... awq_v2_ext.gemv_forward_cuda_decode   awq/modules/linear/gemv_fast.py:192-201
+ *                                   awq_v2_ext.gemm_forward_cuda_prefill  awq/modules/linear/gemv_fast.py:203-205
+ *   b200awq_rmsnorm .............. awq_ext.layernorm_forward_cuda   awq/modules/fused/norm.py:33-36
+ *   b200awq_silu_and_mul ......... awq_ext.silu_and_mul             awq/modules/fused/moe.py:76
+ *
+ * Tensor layouts:
+ *   GEMM  : qweight [K, N/8] i32 (AWQ interleave), qzeros [K/G, N/8] i32, scales [K/G, N] f16
+ *   GEMV  : qweight [N, K/8] i32 (sequential),     qzeros [N, zw] i32,    scales [N, 8*zw] f16
+ *   FAST  : qweight [N/4, K] i16,                  szeros [8*zw, N] f16 (= -z*s), scales [8*zw, N] f16
+ */
+#ifndef B200AWQ_H_
+#define B200AWQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200AWQ_ABI_VERSION 1
+
+typedef void* b200awq_stream_t; /* cudaStream_t */
+
+enum {
+  B200AWQ_OK = 0,
+  B200AWQ_EINVAL = 1,      /* bad shape / null pointer / misaligned pointer */
+  B200AWQ_EUNSUPPORTED = 2,/* shape outside the implemented envelope (e.g. K % 64 != 0 on the tensor-core path) */
+  B200AWQ_EWORKSPACE = 3,  /* workspace missing or too small */
+  B200AWQ_ECUDA = 4,       /* a CUDA runtime / driver call failed */
+  B200AWQ_EARCH = 5        /* device is not sm_100 */
+};
+
+int b200awq_abi_version(void);
+const char* b200awq_error_string(int code);
+/* last CUDA error text seen by this library on the calling thread ("" if none) */
+const char* b200awq_last_cuda_error(void);
+
+/* Bytes of scratch the forward entry points may need for (M, K, N) (split-K partials + tickets).
+ * The caller allocates once (zero-initialised!) and passes it to every call; the library restores the
+ * all-zero ticket state before each kernel exits, so one buffer serves any number of calls on one stream. */
+size_t b200awq_workspace_bytes(int M, int K, int N);
+
+/* W[K, N] f16 = (nibble - zero_nibble) * scale, bit-exact with awq/utils/packing_utils.py:87-102. */
+int b200awq_dequantize_gemm(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out_f16,
+                            int K, int N, int group_size, b200awq_stream_t stream);
+
+/* Y[M, N] f16 = X[M, K] f16 . deq(W) (+ bias[N] f16 if non-null), GEMM layout.  ldx = row pitch of X in
+ * elements (>= K).  M <= 8 runs the CUDA-core GEMV, larger M the tcgen05 tensor-core kernel. */
+int b200awq_gemm_forward(const void* x, int64_t ldx, const int32_t* qweight, const void* scales,
+                         const int32_t* qzeros, const void* bias, void* y, int M, int K, int N, int group_size,
+                         void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
+
+/* Same contraction on the GEMV layout (WQLinear_GEMV buffers). */
+int b200awq_gemv_forward(const void* x, int64_t ldx, const int32_t* qweight, const void* scales,
+                         const int32_t* qzeros, const void* bias, void* y, int M, int K, int N, int group_size,
+                         void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
+
+/* Same contraction on the GEMVFast layout (WQLinear_GEMVFast buffers; W = q*s + szeros). */
+int b200awq_fast_forward(const void* x, int64_t ldx, const int16_t* qweight, const void* scales,
+                         const void* scaled_zeros, const void* bias, void* y, int M, int K, int N, int group_size,
+                         void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
+
+/* out[r, :] = x[r, :] * rsqrt(mean(x[r, :]^2) + eps) * weight   (fp32 math, fp16 in/out; out may alias x) */
+int b200awq_rmsnorm(const void* x, const void* weight, void* out, int rows, int hidden, float eps,
+                    b200awq_stream_t stream);
+
+/* out[r, j] = silu(gate_up[r, j]) * gate_up[r, d + j], j < d  (fp32 math, fp16 in/out) */
+int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200awq_stream_t stream);
+
+/* Tuning / debug knobs (process-global; used by the micro-benchmarks and layout self-tests).
+ *   key 0: GEMV K-rows per CTA override (0 = heuristic)
+ *   key 1: tensor-core path split-K override (0 = heuristic)
+ *   key 2: M threshold at or below which the CUDA-core GEMV is used (default 8)
+ *   key 3: UMMA A-descriptor variant (self-test only)
+ */
+int b200awq_set_knob(int key, int value);
+int b200awq_get_knob(int key);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AWQ_H_ */

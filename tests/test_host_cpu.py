@@ -1,0 +1,163 @@
+"""CPU-only checks of the host side: packed-format producers vs the reference's outputs, the C oracle vs
+the numpy oracle, the torch timing port, and that libb200awq.so loads and exports the whole C ABI."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import awq_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint16)
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+
+    g.build()
+    return True
+
+
+# ------------------------------------------------------------------------------------ packers
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_packers_match_reference_from_linear(golden_dir, tag, built):
+    from autoawq_b200 import packing as P
+
+    g = np.load(os.path.join(golden_dir, "packers.npz"))
+    K, N, G = (int(v) for v in g[f"{tag}_meta"])
+    w = torch.from_numpy(g[f"{tag}_weight"])
+    s = torch.from_numpy(g[f"{tag}_scales_ng"]).float()
+    z = torch.from_numpy(g[f"{tag}_zeros_ng"]).float()
+    iw = P.quantize_to_int(w, s, z, G)
+    assert int(iw.min()) >= 0 and int(iw.max()) <= 15
+    qw, qz, sc = P.pack_gemm(iw, z, s)
+    assert np.array_equal(qw.numpy(), g[f"{tag}_gemm_qweight"])
+    assert np.array_equal(qz.numpy(), g[f"{tag}_gemm_qzeros"])
+    assert np.array_equal(_bits(sc.numpy()), _bits(g[f"{tag}_gemm_scales"]))
+    vw, vz, vs = P.pack_gemv(iw, z, s, G)
+    assert np.array_equal(vw.numpy(), g[f"{tag}_gemv_qweight"])
+    assert np.array_equal(vz.numpy(), g[f"{tag}_gemv_qzeros"])
+    assert np.array_equal(_bits(vs.numpy()), _bits(g[f"{tag}_gemv_scales"]))
+    if f"{tag}_fast_qweight" in g:
+        fw, fs, fz = P.pack_gemv_fast(iw, z, s, G)
+        assert np.array_equal(fw.numpy(), g[f"{tag}_fast_qweight"])
+        assert np.array_equal(_bits(fs.numpy()), _bits(g[f"{tag}_fast_scales"]))
+        assert np.array_equal(_bits(fz.numpy()), _bits(g[f"{tag}_fast_qzeros"]))
+    assert np.array_equal(P.unpack_gemm_words(qw).numpy(), iw.t().numpy().astype(np.uint8))
+
+
+def test_zeros_width(golden_dir, built):
+    from autoawq_b200.packing import calculate_zeros_width
+
+    g = np.load(os.path.join(golden_dir, "packers.npz"))
+    for (k, gs), zw in zip(g["zw_in"], g["zw_out"]):
+        assert calculate_zeros_width(int(k), int(gs)) == int(zw)
+
+
+def test_module_mirrors_have_reference_buffers(built):
+    """Buffer names / shapes / dtypes are the checkpoint contract (gemm.py:135-169, gemv.py:45-74,
+    gemv_fast.py:86-125)."""
+    from autoawq_b200.linear import WQLinear_GEMM, WQLinear_GEMV, WQLinear_GEMVFast
+
+    m = WQLinear_GEMM(4, 128, 4096, 1792, True, "cpu")
+    assert m.qweight.shape == (4096, 224) and m.qweight.dtype == torch.int32
+    assert m.qzeros.shape == (32, 224) and m.scales.shape == (32, 1792) and m.bias.shape == (1792,)
+    assert set(dict(m.named_buffers())) == {"qweight", "qzeros", "scales", "bias"}
+    v = WQLinear_GEMV(4, 128, 14336, 4096, False, "cpu")
+    assert v.qweight.shape == (4096, 1792) and v.qzeros.shape == (4096, 14) and v.scales.shape == (4096, 112)
+    assert v.split_k_iters == 8 and v.bias is None
+    f = WQLinear_GEMVFast(4, 128, 4096, 4096, False, "cpu")
+    assert f.qweight.shape == (1024, 4096) and f.qweight.dtype == torch.int16
+    assert f.scales.shape == (32, 4096) and f.qzeros.dtype == torch.float16
+    with pytest.raises(NotImplementedError):
+        WQLinear_GEMM(8, 128, 256, 256, False, "cpu")
+    with pytest.raises(AssertionError):
+        WQLinear_GEMM(4, 128, 200, 256, False, "cpu")
+    m2 = WQLinear_GEMM(4, -1, 256, 64, False, "cpu")
+    assert m2.group_size == 256 and m2.qzeros.shape == (1, 8)
+
+
+def test_no_cpu_fallback(built):
+    """The product path refuses CPU tensors instead of silently computing on the host."""
+    from autoawq_b200 import ext
+    from autoawq_b200.linear import WQLinear_GEMM
+
+    m = WQLinear_GEMM(4, 128, 256, 64, False, "cpu")
+    with pytest.raises(ext.B200AwqError):
+        m(torch.zeros(1, 1, 256, dtype=torch.float16))
+    with pytest.raises(ext.B200AwqError):
+        ext.dequantize_weights_cuda(m.qweight, m.scales, m.qzeros, 0, 0, 0, False)
+
+
+def test_product_does_not_import_oracle():
+    for pkg in ("autoawq_b200", "awq_ext", "awq_v2_ext"):
+        for dp, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dp, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{pkg}/{f} imports the oracle"
+                    if f != "build.py":  # build.py compiles the checker (building it is not using it)
+                        assert "awq_oracle" not in src and "libawqoracle" not in src, f"{pkg}/{f} uses the oracle"
+
+
+# ---------------------------------------------------------------------------------- C ABI
+def test_cabi_exports_every_declared_symbol(built):
+    from autoawq_b200 import _cabi
+
+    header = open(os.path.join(ROOT, "include", "b200awq.h")).read()
+    declared = set(re.findall(r"\b(b200awq_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_cabi.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b200awq.h but not exported"
+    assert declared == set(_cabi.SIGNATURES), "ctypes table and header disagree"
+    assert _cabi.lib.b200awq_abi_version() == 1
+    assert _cabi.lib.b200awq_error_string(3).decode().startswith("workspace")
+    assert _cabi.lib.b200awq_workspace_bytes(1, 4096, 4096) == 16384 + 4096 * 4
+    assert _cabi.lib.b200awq_workspace_bytes(4096, 4096, 4096) == 16384 + 64 * 4096 * 4
+
+
+def test_cabi_argument_validation_without_gpu(built):
+    """Shape / pointer validation happens before any CUDA call, so it is checkable on the CPU box."""
+    from autoawq_b200._cabi import lib
+
+    assert lib.b200awq_gemm_forward(None, 4096, None, None, None, None, None, 1, 4096, 4096, 128, None, 0, None) == 1
+    assert lib.b200awq_gemm_forward(None, 4096, None, None, None, None, None, 1, 4096, 4095, 128, None, 0, None) == 1
+    assert lib.b200awq_gemm_forward(None, 4096, None, None, None, None, None, 1, 4096, 4096, 100, None, 0, None) == 1
+    assert lib.b200awq_gemm_forward(None, 4096, None, None, None, None, None, 0, 4096, 4096, 128, None, 0, None) == 0
+    assert lib.b200awq_dequantize_gemm(None, None, None, None, 128, 64, 128, None) == 1
+    assert lib.b200awq_set_knob(99, 1) == 1 and lib.b200awq_get_knob(2) == 8
+
+
+# ------------------------------------------------------------------------------- C oracle
+def test_c_oracle_matches_numpy_oracle(built):
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libawqoracle.so"))
+    for (K, N, G, raw) in [(256, 64, 128, False), (128, 40, 32, True), (384, 72, 128, True)]:
+        c = O.make_case(K, N, G, seed=9, raw=raw)
+        out = np.empty((K, N), dtype=np.uint16)
+        lib.oracle_dequantize_gemm(
+            c["qweight"].ctypes.data_as(ctypes.c_void_p), c["qzeros"].ctypes.data_as(ctypes.c_void_p),
+            c["scales"].ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), K, N, G)
+        w = O.dequantize_gemm(c["qweight"], c["qzeros"], c["scales"], G)
+        assert np.array_equal(out, _bits(w))
+        x = np.random.default_rng(0).standard_normal((3, K)).astype(np.float16)
+        y = np.empty((3, N), dtype=np.float64)
+        lib.oracle_gemm_f64(x.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p),
+                            y.ctypes.data_as(ctypes.c_void_p), 3, K, N)
+        np.testing.assert_allclose(y, O.gemm_f64(x, w), rtol=1e-12, atol=1e-12)
+
+
+def test_torch_port_matches_oracle():
+    from oracle import ref_cpu_path as R
+
+    c = O.make_case(256, 64, 64, seed=4, raw=True)
+    w = R.dequantize(torch.from_numpy(c["qweight"]), torch.from_numpy(c["qzeros"]), torch.from_numpy(c["scales"]), 64)
+    assert w.dtype == torch.float16
+    assert np.array_equal(_bits(w.numpy()), _bits(O.dequantize_gemm(c["qweight"], c["qzeros"], c["scales"], 64)))
