@@ -68,8 +68,9 @@ def _x2d(x: torch.Tensor, K: int) -> torch.Tensor:
     if x.shape[-1] != K:
         raise B200AwqError(f"b200awq: activation feature dim {x.shape[-1]} != in_features {K}")
     x2 = x.reshape(-1, K)
-    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < K):
-        x2 = x2.contiguous()
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and (x2.stride(0) < K or x2.stride(0) % 8 != 0)) \
+            or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()  # TMA needs 16-byte aligned rows
     return x2
 
 
