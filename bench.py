@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py - Llama-3-8B W4A16 decode (default) / prefill throughput of the AWQ linear path on B200.
+
+A "step" is one pass of the hot path over one batch of synthetic input: every quantised linear of
+Llama-3-8B (32 layers x [qkv 4096->6144, o 4096->4096, gate|up 4096->28672, down 14336->4096], GEMM
+layout, group 128, random-init AWQ-packed weights, 3.63 GB per replica >> the 126 MB L2, so every step
+streams the weights from HBM) plus the RMSNorm / SiLU*mul glue kernels that keep the activations O(1).
+Attention, KV cache, embeddings and lm_head are not on the path (BASELINE.json north_star:
+"awq/modules/fused/* sits unchanged on top", "synthetic Llama-shape activations").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode decode|prefill] [--impl reference]
+
+One JSON line on stdout (rank 0).  value = whole-job tokens/s with inputs resident in HBM (CUDA-graph
+replay of the plugin calls); e2e = the same step driven from pinned HOST buffers through the
+awq_ext-facing operator calls (H2D of the token's hidden state and D2H of the result inside the timed
+region); roofline = the GEMV (decode) or tcgen05 GEMM (prefill) kernels alone against MEASURED_PEAKS.json;
+cpu_baseline / --impl reference = the reference's CPU path (dequantize_gemm + torch.matmul,
+awq/modules/linear/gemm.py:71-77) restated in oracle/ref_cpu_path.py, timed on the host cores on a
+bounded sample (whole layers), extrapolated to the 32-layer step.
+N > 1: Llama-3-8B fits one GPU, so ranks are independent replicas (no data-path collective, weak
+scaling); the tensor-parallel column/row sharding for models that exceed one GPU is autoawq_b200/shard.py.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIDDEN, INTER, LAYERS, QKV_N, GROUP = 4096, 14336, 32, 6144, 128
+LINEARS = [("qkv", HIDDEN, QKV_N), ("o", HIDDEN, HIDDEN), ("gate_up", HIDDEN, 2 * INTER), ("down", INTER, HIDDEN)]
+
+
+def linear_bytes(K, N, M, G=GROUP):
+    """Algorithmic bytes of one W4A16 linear: packed weights + scales + zeros + x + y."""
+    return K * N // 2 + (K // G) * N * 2 + (K // G) * N // 2 + 2 * M * K + 2 * M * N
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = float(f[1])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[0]))
+                    for nm, v in zip(names, f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+            except ValueError:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+class Replica:
+    """Random-init AWQ-packed Llama-3-8B linears on one GPU + the step that chains them."""
+
+    def __init__(self, dev, M, layers=LAYERS, seed=0):
+        import torch
+
+        from autoawq_b200 import ext
+
+        self.torch, self.ext, self.dev, self.M, self.layers = torch, ext, dev, M, layers
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.w = []
+        for _ in range(layers):
+            lw = {}
+            for name, K, N in LINEARS:
+                qw = torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, device=dev, generator=g)
+                qz = torch.randint(-2**31, 2**31 - 1, (K // GROUP, N // 8), dtype=torch.int32, device=dev, generator=g)
+                # (q - z) has std ~6.1: keep std(W) * sqrt(K) ~ 1 so activations stay O(1) down the chain
+                s = (torch.rand((K // GROUP, N), device=dev, generator=g) * 0.5 + 0.75) / (6.1 * K**0.5)
+                lw[name] = (qw, s.half(), qz)
+            self.w.append(lw)
+        self.norm_w = torch.ones(HIDDEN, dtype=torch.float16, device=dev)
+        self.xn = torch.empty((M, HIDDEN), dtype=torch.float16, device=dev)
+        self.act = torch.empty((M, INTER), dtype=torch.float16, device=dev)
+        self.h = torch.randn((M, HIDDEN), generator=g, device=dev, dtype=torch.float16)
+        self.out = torch.empty((M, HIDDEN), dtype=torch.float16, device=dev)
+        self.launches_per_step = layers * 7
+
+    def lin(self, x, w):
+        # the awq_ext-facing operator (awq_ext.gemm_forward_cuda semantics; autoawq_b200/ext.py)
+        return self.ext.gemm_forward_cuda(x, w[0], w[1], w[2], 8)
+
+    def step(self, h):
+        e = self.ext
+        for lw in self.w:
+            e.layernorm_forward_cuda(h, self.norm_w, self.xn, 1e-5)
+            qkv = self.lin(self.xn, lw["qkv"])
+            o = self.lin(qkv[:, :HIDDEN], lw["o"])
+            e.layernorm_forward_cuda(o, self.norm_w, self.xn, 1e-5)
+            gu = self.lin(self.xn, lw["gate_up"])
+            e.silu_and_mul(self.act, gu)
+            h = self.lin(self.act, lw["down"])
+        return h
+
+    def gemm_only(self, h):
+        """The quantised linears alone (roofline leg): same weights, fixed inputs, no glue kernels."""
+        for lw in self.w:
+            self.lin(self.xn, lw["qkv"])
+            self.lin(self.xn, lw["o"])
+            self.lin(self.xn, lw["gate_up"])
+            self.lin(self.act, lw["down"])
+
+
+def capture(torch, fn):
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        res = fn()
+    return g, res
+
+
+def timed(torch, fn, steps, warmup, dist=None):
+    """W untimed + K timed calls of fn, CUDA events on the launching stream, barrier + sync both sides,
+    max over ranks.  Returns seconds for the K steps."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sec = e0.elapsed_time(e1) / 1e3
+    if dist is not None:
+        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    return sec
+
+
+def cpu_reference_sample(M, layers_sample, reps, threads=None):
+    """Reference CPU path on a bounded sample: `layers_sample` whole layers of the step, fp16,
+    all host threads.  Returns (seconds per sampled layer, cores)."""
+    import torch
+
+    from oracle import ref_cpu_path as R
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    ws = []
+    for name, K, N in LINEARS:
+        qw = torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, generator=g)
+        qz = torch.randint(-2**31, 2**31 - 1, (K // GROUP, N // 8), dtype=torch.int32, generator=g)
+        s = ((torch.rand((K // GROUP, N), generator=g) * 0.5 + 0.75) / (6.1 * K**0.5)).half()
+        ws.append((K, N, qw, qz, s))
+    xs = {K: torch.randn((M, K), generator=g, dtype=torch.float16) for K in (HIDDEN, INTER)}
+    ts = []
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            for _l in range(layers_sample):
+                for K, N, qw, qz, s in ws:
+                    R.wqlinear_forward(xs[K], qw, qz, s, GROUP)
+            ts.append((time.perf_counter() - t0) / layers_sample)
+    return min(ts), cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--mode", choices=["decode", "prefill"], default="decode")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: fewer layers => INVALID as a bench value")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    M = 1 if a.mode == "decode" else 4096
+    tokens_per_step = M
+    metric = f"{a.mode} tok/s Llama-3-8B W4A16 (quantised linears, bs=1" + (", seq=1)" if M == 1 else ", seq=4096)")
+    config = {"workload": f"Llama-3-8B W4A16 GEMM-layout g128, {a.mode} bs=1 seq={M}: 32 layers x "
+                          "[rmsnorm, qkv 4096x6144, o 4096x4096, rmsnorm, gate|up 4096x28672, silu*mul, down 14336x4096]",
+              "weights": "random-init AWQ-packed, distinct per layer (3.63 GB/replica)",
+              "l2": "inputs larger than L2: 3.63 GB of weights streamed per step vs 126 MB L2",
+              "parallelism": f"replicas x{a.gpus}" if a.gpus > 1 else "single GPU", "layers": a.layers}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        layers_sample = 1
+        per_layer = []
+        cores = os.cpu_count() or 1
+        for i in range(a.warmup + a.steps):
+            t, cores = cpu_reference_sample(M if M == 1 else 64, layers_sample, 1)
+            if i >= a.warmup:
+                per_layer.append(t)
+            if M == 1 and sum(per_layer) > 150:
+                break
+        mean_layer = sum(per_layer) / len(per_layer)
+        m_eff = M if M == 1 else 64
+        val = m_eff / (mean_layer * LAYERS)
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": "tok/s", "n_gpus": a.gpus,
+                "steps": len(per_layer), "warmup": a.warmup, "ms_per_step": mean_layer * LAYERS * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": val, "unit": "tok/s", "cores": cores, "kind": "port",
+                                 "sample": f"{layers_sample} of 32 layers per step (4 linears, dequantize_gemm + "
+                                           f"torch.matmul fp16, M={m_eff}), x32 extrapolated"},
+                "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------------- B200 arm
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    rep = Replica(dev, M, layers=a.layers, seed=rank)
+    peaks = measured_peaks()
+
+    # value leg: inputs resident in HBM, the step replayed as one CUDA graph
+    g_step, out_static = capture(torch, lambda: rep.step(rep.h))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_wall0 = time.time()
+    sec = timed(torch, g_step.replay, a.steps, a.warmup, dist)
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    value = world * tokens_per_step * a.steps / sec
+
+    # roofline leg: the quantised-linear kernels alone, same weights
+    g_lin, _ = capture(torch, lambda: rep.gemm_only(rep.h))
+    sec_lin = timed(torch, g_lin.replay, a.steps, a.warmup, dist)
+    n_lin = 4 * a.layers
+    alg_bytes = sum(linear_bytes(K, N, M) for _, K, N in LINEARS) * a.layers
+    alg_flops = sum(2.0 * M * K * N for _, K, N in LINEARS) * a.layers
+    avg_launch_s = sec_lin / a.steps / n_lin
+    if a.mode == "decode":
+        ach = alg_bytes / n_lin / avg_launch_s / 1e9
+        roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
+                "kernel": "gemv_gemm_layout_kernel<4,1,16,8,16>", "peak_src": peaks["src"] + " (hbm_gbs)",
+                "per_launch": {"avg_us": round(avg_launch_s * 1e6, 2), "alg_bytes": alg_bytes // n_lin,
+                               "launches_timed": n_lin * a.steps,
+                               "how": "CUDA events around a graph of the 128 linear launches of one step"}}
+    else:
+        ach = alg_flops / n_lin / avg_launch_s / 1e12
+        pk = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "achieved": round(ach, 1), "peak": pk, "unit": "TFLOP/s",
+                "frac": round(ach / pk, 4), "traffic": None, "kernel": "gemm_tc_kernel<256,0>",
+                "peak_src": peaks["src"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
+                "per_launch": {"avg_us": round(avg_launch_s * 1e6, 2), "alg_flops": alg_flops / n_lin,
+                               "launches_timed": n_lin * a.steps}}
+
+    # e2e leg: host buffers, H2D + plugin calls + D2H inside the timed region
+    h_host = torch.randn((M, HIDDEN), dtype=torch.float16).pin_memory()
+    y_host = torch.empty((M, HIDDEN), dtype=torch.float16).pin_memory()
+
+    def e2e_step():
+        rep.h.copy_(h_host, non_blocking=True)
+        g_step.replay()
+        y_host.copy_(out_static, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    sec_e2e = timed(torch, e2e_step, a.steps, a.warmup, dist)
+    e2e_val = world * tokens_per_step * a.steps / sec_e2e
+
+    # eager plugin calls (no graph): what a Python caller that does not capture graphs sees
+    def eager_step():
+        rep.h.copy_(h_host, non_blocking=True)
+        y = rep.step(rep.h)
+        y_host.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    n_eager = max(3, a.steps // 5)
+    sec_eager = timed(torch, eager_step, n_eager, 2, dist)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    # CPU baseline on rank 0, N = 1 only (bounded sample)
+    cpu = None
+    if world == 1:
+        t_layer, cores = cpu_reference_sample(M if M == 1 else 64, 1, 2)
+        m_eff = M if M == 1 else 64
+        cpu = {"value": m_eff / (t_layer * LAYERS), "unit": "tok/s", "cores": cores, "kind": "port",
+               "sample": f"1 of 32 layers (4 linears, dequantize_gemm + torch.matmul fp16, M={m_eff}), best of 2, x32"}
+    config["e2e_eager_tok_s"] = round(world * tokens_per_step * n_eager / sec_eager, 1)
+    config["value_leg"] = "CUDA-graph replay of the awq_ext-facing operator calls, inputs resident in HBM"
+    line = {"metric": metric, "value": round(value, 2), "unit": "tok/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": round(sec / a.steps * 1e3, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config,
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_val, 2), "unit": "tok/s", "h2d_bytes_per_step": M * HIDDEN * 2,
+                    "d2h_bytes_per_step": M * HIDDEN * 2},
+            "gpu_launches": rep.launches_per_step * a.steps,
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
