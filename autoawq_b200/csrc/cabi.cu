@@ -97,9 +97,9 @@ int b200awq_gemm_forward(const void* x, int64_t ldx, const int32_t* qweight, con
   Ws ws;
   const bool have_ws = carve(workspace, workspace_bytes, M, N, &ws);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (M <= knob(2)) {
+  if (M <= knob(2) && M <= 8 && gemv_gemm_layout_supported(a)) {
     if (!have_ws) return B200AWQ_EWORKSPACE;  // the GEMV splits K across CTAs
-    if ((N + 7) / 8 > 4096 * 8) return B200AWQ_EUNSUPPORTED;
+    if ((N + 255) / 256 > 4096) return B200AWQ_EUNSUPPORTED;
     return fold(gemv_gemm_layout(a, ws.acc, ws.tickets, st));
   }
   return fold(gemm_tc(a, 0, ws.acc, ws.tickets, st));

@@ -9,10 +9,11 @@
 //               consecutive k of one n).
 //   B operand = X tile [BT tokens x 64 k], K-major, 128B swizzle, loaded by TMA (cp.async.bulk.tensor.2d).
 //   D         = [128 lanes (n) x BT columns (tokens)] fp32 in tensor memory.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = dequant producers, then epilogue (tcgen05.ld -> +bias -> fp16 -> global).
-// Pipeline: NS smem stages, one "full" mbarrier per stage (128 dequant arrivals + 1 TMA expect_tx),
-// one "empty" mbarrier per stage (tcgen05.commit), tmem_full / tmem_empty between MMA and epilogue.
+// Warp roles (448 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> +bias -> fp16 -> global), warps 6..13 = dequant producers.
+// Pipeline: NS smem stages, one "full" mbarrier per stage (256 dequant arrivals + 1 TMA expect_tx),
+// one "empty" mbarrier per stage (tcgen05.commit); two TMEM accumulator buffers with tmem_full /
+// tmem_empty mbarriers, so the epilogue of one tile overlaps the main loop of the next.
 // Persistent CTAs walk (n_tile, m_tile, k_split) work items.  Split-K (only for M <= 64, where the
 // problem is HBM-bound and 148 SMs must all stream weights) reduces through fp32 atomics into the
 // caller's zeroed workspace; the last CTA of a tile rounds to fp16 and restores the zeros.
@@ -49,7 +50,7 @@ struct TcCfg {
   static constexpr int kXStageBytes = BT * kBK * 2;
   static constexpr int kStageBytes = kAStageBytes + kXStageBytes;
   static constexpr int kStages = (BT >= 256) ? 4 : (BT >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = BT < 32 ? 32 : BT;
+  static constexpr int kTmemCols = 2 * (BT < 32 ? 32 : BT);  // two accumulator buffers
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -58,79 +59,99 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // ------------------------------------------------------------------------------- A-tile producers
-// GEMM layout: thread dt owns word column c = dt % 16 (8 n) and rows kk = dt/16 + 8 j.
+// 256 producer threads (8 warps).  load() issues the global loads of one k-step (packed words plus,
+// when the quantisation group changes, the group's zeros / scales) ONE STEP AHEAD of store(), which
+// dequantises from registers and writes the swizzled fp16 tile: no global latency on the critical path.
+constexpr int kProducers = 256;
+
+// GEMM layout: thread dt owns word column c = dt % 16 (8 n) and rows kk = dt/16 + 16 j, j = 0..3.
 struct GemmLayoutLoader {
-  uint32_t q[8];
+  uint32_t q[4];
+  uint32_t zq[2];
+  uint4 sc[2];
+  int gidx[2];
+  __device__ __forceinline__ void init() { gidx[0] = gidx[1] = -1; zq[0] = zq[1] = 0; sc[0] = sc[1] = make_uint4(0, 0, 0, 0); }
   __device__ __forceinline__ void load(const TcParams& p, int nt, int k0, int dt) {
     const int NW = p.N >> 3;
     const int c = dt & 15, rb = dt >> 4;
     const int wc = nt * 16 + c;
     const bool ok = wc < NW;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       q[j] = 0u;
-      if (ok) q[j] = ldg_stream_u1(p.qweight + (int64_t)(k0 + rb + 8 * j) * NW + wc);
+      if (ok) q[j] = ldg_stream_u1(p.qweight + (int64_t)(k0 + rb + 16 * j) * NW + wc);
+    }
+    // rows j = 0,1 (< 32) and j = 2,3 (>= 32) may sit in different groups when G == 32
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = (k0 + rb + 32 * h) / p.G;
+      if (g != gidx[h]) {
+        gidx[h] = g;
+        if (ok) {
+          zq[h] = static_cast<uint32_t>(__ldg(p.qzeros + (int64_t)g * NW + wc));
+          sc[h] = __ldg(reinterpret_cast<const uint4*>(p.scales + (int64_t)g * p.N + wc * 8));
+        }
+      }
     }
   }
   __device__ __forceinline__ void store(const TcParams& p, int nt, int k0, int dt, uint8_t* a_stage) const {
-    const int NW = p.N >> 3;
     const int c = dt & 15, rb = dt >> 4;
-    const int wc = nt * 16 + c;
-    const bool ok = wc < NW;
-    int cur_g = -1;
-    ZeroPairs zp;
-    uint4 sc = make_uint4(0, 0, 0, 0);
+    const bool ok = (nt * 16 + c) < (p.N >> 3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (k0 + rb + 8 * j) / p.G;
-      if (g != cur_g) {
-        cur_g = g;
-        if (ok) {
-          zp = awq_zero_pairs(static_cast<uint32_t>(p.qzeros[(int64_t)g * NW + wc]));
-          sc = *reinterpret_cast<const uint4*>(p.scales + (int64_t)g * p.N + wc * 8);
-        } else {
-          zp = awq_zero_pairs(0u);
-        }
+    for (int h = 0; h < 2; ++h) {
+      const ZeroPairs zp = awq_zero_pairs(zq[h]);
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = 2 * h + jj;
+        uint4 o = awq_dequant_word(q[j], zp, sc[h]);
+        if (!ok) o = make_uint4(0, 0, 0, 0);
+        // MN-major SW128: (n/64)*8192 + (k/8)*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 ; k = rb + 16 j
+        const uint32_t off = (uint32_t)(c >> 3) * 8192u + (uint32_t)(2 * j + (rb >> 3)) * 1024u +
+                             (uint32_t)(rb & 7) * 128u + (uint32_t)(((c & 7) ^ (rb & 7)) << 4);
+        *reinterpret_cast<uint4*>(a_stage + off) = o;
       }
-      uint4 o = awq_dequant_word(q[j], zp, sc);
-      if (!ok) o = make_uint4(0, 0, 0, 0);
-      // MN-major SW128: (n/64)*8192 + (k/8)*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 ; k = rb + 8j
-      const uint32_t off = (uint32_t)(c >> 3) * 8192u + (uint32_t)j * 1024u + (uint32_t)rb * 128u +
-                           (uint32_t)(((c & 7) ^ rb) << 4);
-      *reinterpret_cast<uint4*>(a_stage + off) = o;
     }
   }
 };
 
-// GEMV layout: thread dt owns k-word cw = dt % 8 (8 consecutive k) and rows n = dt/8 + 16 j.
+// GEMV layout: thread dt owns k-word cw = dt % 8 (8 consecutive k) and rows n = dt/8 + 32 j, j = 0..3.
 struct GemvLayoutLoader {
-  uint32_t q[8];
+  uint32_t q[4];
+  uint32_t zs[4];  // per row: fp16 scale in the low half, zero-point (0..15) in the high half
+  int gidx;
+  __device__ __forceinline__ void init() { gidx = -1; zs[0] = zs[1] = zs[2] = zs[3] = 0; }
   __device__ __forceinline__ void load(const TcParams& p, int nt, int k0, int dt) {
     const int KW = p.K >> 3;
     const int cw = dt & 7, rb = dt >> 3;
+    const int g = (k0 + cw * 8) / p.G;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = nt * kTileN + rb + 16 * j;
+    for (int j = 0; j < 4; ++j) {
+      const int n = nt * kTileN + rb + 32 * j;
       q[j] = 0u;
-      if (n < p.N) q[j] = ldg_stream_u1(p.qweight + (int64_t)n * KW + (k0 >> 3) + cw);
+      if (n < p.N) {
+        q[j] = ldg_stream_u1(p.qweight + (int64_t)n * KW + (k0 >> 3) + cw);
+        if (g != gidx) {
+          const uint32_t s = __half_as_ushort(__ldg(p.scales + (int64_t)n * (p.zw * 8) + g));
+          const uint32_t zword = static_cast<uint32_t>(__ldg(p.qzeros + (int64_t)n * p.zw + (g >> 3)));
+          zs[j] = s | (((zword >> (4 * (g & 7))) & 0xFu) << 16);
+        }
+      }
     }
+    gidx = g;
   }
   __device__ __forceinline__ void store(const TcParams& p, int nt, int k0, int dt, uint8_t* a_stage) const {
     const int cw = dt & 7, rb = dt >> 3;
-    const int g = (k0 + cw * 8) / p.G;
     const __half2 r16 = __float2half2_rn(0.0625f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int nl = rb + 16 * j;
+    for (int j = 0; j < 4; ++j) {
+      const int nl = rb + 32 * j;
       const int n = nt * kTileN + nl;
       uint4 o = make_uint4(0, 0, 0, 0);
       if (n < p.N) {
-        const __half s = p.scales[(int64_t)n * (p.zw * 8) + g];
-        const uint32_t zword = static_cast<uint32_t>(p.qzeros[(int64_t)n * p.zw + (g >> 3)]);
-        const float zf = static_cast<float>((zword >> (4 * (g & 7))) & 0xFu);
+        const float zf = static_cast<float>(zs[j] >> 16);
         const __half2 zA = __float2half2_rn(1024.f + zf);   // exact
         const __half2 zB = __float2half2_rn(-(64.f + zf));  // exact
-        const __half2 s2 = __half2half2(s);
+        const __half2 s2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(zs[j] & 0xffffu)));
         RawPairs r = awq_raw_pairs(q[j]);
         // pairs (k0,k4) (k1,k5) (k2,k6) (k3,k7)
         const uint32_t d0 = h2_as_u32(__hmul2(__hsub2(u32_as_h2(r.p[0]), zA), s2));
@@ -149,50 +170,52 @@ struct GemvLayoutLoader {
   }
 };
 
-// GEMVFast layout: thread dt owns row n = dt of the tile (row group dt/4, run dt%4): 2 x 16 B = 64 k.
+// GEMVFast layout: thread dt owns row n = dt/2 of the tile and the 32-k half h = dt%2 of the step.
 struct FastLayoutLoader {
-  uint4 q[2];
+  uint4 q;
+  uint32_t ss;  // scale (low half) | scaled zero (high half)
+  int gidx;
+  __device__ __forceinline__ void init() { gidx = -1; ss = 0; }
   __device__ __forceinline__ void load(const TcParams& p, int nt, int k0, int dt) {
-    const int n = nt * kTileN + dt;
-    q[0] = q[1] = make_uint4(0, 0, 0, 0);
+    const int n = nt * kTileN + (dt >> 1), h = dt & 1;
+    q = make_uint4(0, 0, 0, 0);
+    const int g = (k0 + 32 * h) / p.G;
     if (n < p.N) {
-      const int16_t* base = reinterpret_cast<const int16_t*>(p.qweight) + (int64_t)(n >> 2) * p.K + (int64_t)k0 +
-                            (n & 3) * 16;  // block k0/64 starts at int16 offset k0
-      q[0] = ldg_stream_u4(base);
-      q[1] = ldg_stream_u4(base + 8);
+      // 64-k block k0/64 of row group n/4 starts at int16 offset k0; run (n%4) * 16; half h * 8
+      q = ldg_stream_u4(reinterpret_cast<const int16_t*>(p.qweight) + (int64_t)(n >> 2) * p.K + (int64_t)k0 +
+                        (n & 3) * 16 + h * 8);
+      if (g != gidx) {
+        const __half* sz_ptr = reinterpret_cast<const __half*>(p.qzeros);
+        ss = static_cast<uint32_t>(__half_as_ushort(__ldg(p.scales + (int64_t)g * p.N + n))) |
+             (static_cast<uint32_t>(__half_as_ushort(__ldg(sz_ptr + (int64_t)g * p.N + n))) << 16);
+      }
     }
+    gidx = g;
   }
   __device__ __forceinline__ void store(const TcParams& p, int nt, int k0, int dt, uint8_t* a_stage) const {
-    const int n = nt * kTileN + dt;
-    const __half* sz_ptr = reinterpret_cast<const __half*>(p.qzeros);
+    const int nl = dt >> 1, h = dt & 1;
+    const bool ok = nt * kTileN + nl < p.N;
     const __half2 r16 = __float2half2_rn(0.0625f);
     const __half2 m1024 = __float2half2_rn(1024.f), m64 = __float2half2_rn(-64.f);
+    const __half2 s2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(ss & 0xffffu)));
+    const __half2 z2 = __half2half2(__ushort_as_half(static_cast<unsigned short>(ss >> 16)));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t d[4][4];  // [word u][r'] : pair (k, k+1), k = 32h + 2u + 8r'
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      __half2 s2 = __float2half2_rn(0.f), z2 = s2;
-      if (n < p.N) {
-        const int g = (k0 + 32 * h) / p.G;
-        s2 = __half2half2(p.scales[(int64_t)g * p.N + n]);
-        z2 = __half2half2(sz_ptr[(int64_t)g * p.N + n]);
-      }
-      const uint32_t w[4] = {q[h].x, q[h].y, q[h].z, q[h].w};
-      uint32_t d[4][4];  // [word u][r']
+    for (int u = 0; u < 4; ++u) {
+      RawPairs r = awq_raw_pairs(w[u]);
+      d[u][0] = h2_as_u32(__hfma2(__hsub2(u32_as_h2(r.p[0]), m1024), s2, z2));
+      d[u][1] = h2_as_u32(__hfma2(__hfma2(u32_as_h2(r.p[1]), r16, m64), s2, z2));
+      d[u][2] = h2_as_u32(__hfma2(__hsub2(u32_as_h2(r.p[2]), m1024), s2, z2));
+      d[u][3] = h2_as_u32(__hfma2(__hfma2(u32_as_h2(r.p[3]), r16, m64), s2, z2));
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        RawPairs r = awq_raw_pairs(w[u]);
-        d[u][0] = h2_as_u32(__hfma2(__hsub2(u32_as_h2(r.p[0]), m1024), s2, z2));
-        d[u][1] = h2_as_u32(__hfma2(__hfma2(u32_as_h2(r.p[1]), r16, m64), s2, z2));
-        d[u][2] = h2_as_u32(__hfma2(__hsub2(u32_as_h2(r.p[2]), m1024), s2, z2));
-        d[u][3] = h2_as_u32(__hfma2(__hfma2(u32_as_h2(r.p[3]), r16, m64), s2, z2));
-      }
-#pragma unroll
-      for (int rp = 0; rp < 4; ++rp) {
-        uint4 o = make_uint4(d[0][rp], d[1][rp], d[2][rp], d[3][rp]);  // k = 32h + 8rp + 0..7
-        if (n >= p.N) o = make_uint4(0, 0, 0, 0);
-        const int cc = 4 * h + rp;
-        const uint32_t off = (uint32_t)dt * 128u + (uint32_t)((cc ^ (dt & 7)) << 4);
-        *reinterpret_cast<uint4*>(a_stage + off) = o;
-      }
+    for (int rp = 0; rp < 4; ++rp) {
+      uint4 o = make_uint4(d[0][rp], d[1][rp], d[2][rp], d[3][rp]);  // k = 32h + 8rp + 0..7
+      if (!ok) o = make_uint4(0, 0, 0, 0);
+      const int cc = 4 * h + rp;
+      const uint32_t off = (uint32_t)nl * 128u + (uint32_t)((cc ^ (nl & 7)) << 4);
+      *reinterpret_cast<uint4*>(a_stage + off) = o;
     }
   }
 };
@@ -204,8 +227,13 @@ template <> struct LoaderOf<1> { using T = GemvLayoutLoader; };
 template <> struct LoaderOf<2> { using T = FastLayoutLoader; };
 
 // --------------------------------------------------------------------------------------- kernel
+// warps: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..5 = epilogue (TMEM lane quadrant = warp % 4),
+// 6..13 = dequant producers.  Two TMEM accumulator buffers: the epilogue of tile i overlaps the main loop
+// of tile i+1.
+constexpr int kTcThreads = 64 + 128 + kProducers;
+
 template <int BT, int LAYOUT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmx, const TcParams p) {
   using Cfg = TcCfg<BT>;
   constexpr int NS = Cfg::kStages;
@@ -216,10 +244,10 @@ __global__ void __launch_bounds__(192, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)NS * Cfg::kStageBytes);
   uint64_t* full = bars;            // [NS]
   uint64_t* empty = bars + NS;      // [NS]
-  uint64_t* tmem_full = bars + 2 * NS;
-  uint64_t* tmem_empty = bars + 2 * NS + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
-  int* s_flag = reinterpret_cast<int*>(bars + 2 * NS + 3);
+  uint64_t* tmem_full = bars + 2 * NS;       // [2]
+  uint64_t* tmem_empty = bars + 2 * NS + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
+  int* s_flag = reinterpret_cast<int*>(bars + 2 * NS + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -227,11 +255,13 @@ __global__ void __launch_bounds__(192, 1)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmx);
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 128 + 1);
+      mbar_init(&full[s], kProducers + 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 128);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -269,12 +299,15 @@ __global__ void __launch_bounds__(192, 1)
       constexpr uint32_t idesc = umma_idesc_f16(kTileN, BT, LAYOUT == 0 ? 1 : 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int it = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
         const int ks = w % p.ksplit;
         const int s_begin = (int)((int64_t)KS * ks / p.ksplit), s_end = (int)((int64_t)KS * (ks + 1) / p.ksplit);
-        mbar_wait(tmem_empty, acc_phase ^ 1);  // epilogue has drained the accumulator
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tmem_empty[buf], use ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BT);
         for (int s = s_begin; s < s_end; ++s) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -285,48 +318,30 @@ __global__ void __launch_bounds__(192, 1)
             uint64_t da, db;
             if (LAYOUT == 0) {
               // MN-major, SW128: LBO = stride between 64-n atoms (8192), SBO = stride between 8-k atoms (1024)
-              if (p.a_desc_variant == 0)
-                da = umma_smem_desc(a_addr + k16 * 2048, 8192, 1024);
-              else
-                da = umma_smem_desc(a_addr + k16 * 2048, 1024, 8192);
+              da = umma_smem_desc(a_addr + k16 * 2048, 8192, 1024);
             } else {
               da = umma_smem_desc(a_addr + k16 * 32, 16, 1024);  // K-major SW128
             }
             db = umma_smem_desc(x_addr + k16 * 32, 16, 1024);    // K-major SW128
-            umma_f16_ss(tmem_base, da, db, idesc, (s > s_begin || k16 > 0) ? 1u : 0u);
+            umma_f16_ss(d_tmem, da, db, idesc, (s > s_begin || k16 > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above retire
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tmem_full);  // accumulator complete
-        acc_phase ^= 1;
+        umma_commit(&tmem_full[buf]);  // accumulator complete
       }
     }
-  } else {
-    // ================================================================= dequant producers + epilogue
-    const int dt = threadIdx.x - 64;  // 0..127
+  } else if (warp < 6) {
+    // ================================================================= epilogue (4 warps)
+    const int et = threadIdx.x - 64;  // 0..127
     const int q4 = warp & 3;          // TMEM lane quadrant this warp may read
-    typename LoaderOf<LAYOUT>::T cur, nxt;
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int ks = w % p.ksplit;
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int mt = (w / p.ksplit) % p.m_tiles;
       const int nt = w / (p.ksplit * p.m_tiles);
-      const int s_begin = (int)((int64_t)KS * ks / p.ksplit), s_end = (int)((int64_t)KS * (ks + 1) / p.ksplit);
-      if (s_begin < s_end) nxt.load(p, nt, s_begin * kBK, dt);
-      for (int s = s_begin; s < s_end; ++s) {
-        cur = nxt;
-        if (s + 1 < s_end) nxt.load(p, nt, (s + 1) * kBK, dt);  // next step's words in flight
-        mbar_wait(&empty[stage], phase ^ 1);
-        cur.store(p, nt, s * kBK, dt, a_base + (size_t)stage * kAStageBytes);
-        fence_proxy_async_smem();
-        mbar_arrive(&full[stage]);
-        if (++stage == NS) { stage = 0; phase ^= 1; }
-      }
-      // ---- epilogue for this work item
-      mbar_wait(tmem_full, acc_phase);
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tmem_full[buf], use);
       tc_fence_after();
       const int n = nt * kTileN + q4 * 32 + lane;
       const bool n_ok = n < p.N;
@@ -335,9 +350,9 @@ __global__ void __launch_bounds__(192, 1)
 #pragma unroll 1
       for (int c0 = 0; c0 < BT; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * BT + c0), v);
         tmem_ld_wait();
-        if (n_ok) {
+        if (n_ok && m0 + c0 < p.M) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int m = m0 + c0 + j;
@@ -352,12 +367,11 @@ __global__ void __launch_bounds__(192, 1)
         }
       }
       tc_fence_before();
-      mbar_arrive(tmem_empty);
-      acc_phase ^= 1;
+      mbar_arrive(&tmem_empty[buf]);
       if (p.ksplit > 1) {
         __threadfence();
         named_bar_sync(1, 128);
-        if (dt == 0) {
+        if (et == 0) {
           const int prev = atomicAdd(&p.tickets[nt * p.m_tiles + mt], 1);
           *s_flag = (prev == p.ksplit - 1);
         }
@@ -376,8 +390,31 @@ __global__ void __launch_bounds__(192, 1)
               p.y[(int64_t)m * p.N + n] = __float2half_rn(f + bias_v);
             }
           }
-          if (dt == 0) p.tickets[nt * p.m_tiles + mt] = 0;
+          if (et == 0) p.tickets[nt * p.m_tiles + mt] = 0;
         }
+      }
+    }
+  } else {
+    // ================================================================= dequant producers (8 warps)
+    const int dt = threadIdx.x - 192;  // 0..255
+    typename LoaderOf<LAYOUT>::T cur, nxt;
+    nxt.init();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const int ks = w % p.ksplit;
+      const int nt = w / (p.ksplit * p.m_tiles);
+      const int s_begin = (int)((int64_t)KS * ks / p.ksplit), s_end = (int)((int64_t)KS * (ks + 1) / p.ksplit);
+      nxt.init();  // new tile: different columns, cached group data is stale
+      if (s_begin < s_end) nxt.load(p, nt, s_begin * kBK, dt);
+      for (int s = s_begin; s < s_end; ++s) {
+        cur = nxt;
+        if (s + 1 < s_end) nxt.load(p, nt, (s + 1) * kBK, dt);  // next step's loads in flight
+        mbar_wait(&empty[stage], phase ^ 1);
+        cur.store(p, nt, s * kBK, dt, a_base + (size_t)stage * kAStageBytes);
+        fence_proxy_async_smem();
+        mbar_arrive(&full[stage]);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -475,7 +512,7 @@ static cudaError_t launch_tc(const CUtensorMap& tm, const TcParams& p, cudaStrea
   }
   const int n_work = p.n_tiles * p.m_tiles * p.ksplit;
   const int grid = n_work < sm_count() ? n_work : sm_count();
-  kern<<<grid, 192, Cfg::kSmemBytes, st>>>(tm, p);
+  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tm, p);
   return cudaGetLastError();
 }
 

@@ -18,162 +18,182 @@ constexpr float kScaleA = 16777216.0f;  // 2^24: code read through mask 0x000f00
 constexpr float kScaleB = 1048576.0f;   // 2^20: code read through mask 0x00f000f0
 
 // ======================================================================= GEMM layout [K, N/8]
-// CTA = TX x TY threads.  Thread (tx, ty) owns WPT consecutive words (8*WPT columns) and RPT consecutive
-// k-rows; a CTA covers TN = 8*WPT*TX columns x KC = RPT*TY rows.  grid = (ceil(N/TN), ceil(K/KC)).
-template <int WPT>
-struct WordVec;
-template <>
-struct WordVec<4> {
-  using T = uint4;
-  static __device__ __forceinline__ void load(const int32_t* p, uint32_t (&w)[4]) {
-    uint4 v = ldg_stream_u4(p);
-    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-  }
-};
-template <>
-struct WordVec<2> {
-  static __device__ __forceinline__ void load(const int32_t* p, uint32_t (&w)[2]) {
-    uint2 v = ldg_stream_u2(p);
-    w[0] = v.x; w[1] = v.y;
-  }
-};
-template <>
-struct WordVec<1> {
-  static __device__ __forceinline__ void load(const int32_t* p, uint32_t (&w)[1]) { w[0] = ldg_stream_u1(p); }
-};
+// v2: the dot products run on the tensor pipe through mma.sync.m16n8k16 with REGISTER-resident fragments.
+// Why: measured on B200, FHFMA issues at ~16 lanes/clk/SM (quarter rate), which caps a CUDA-core fp32
+// GEMV at ~1.7 TB/s (26% of HBM peak); feeding the same registers to HMMA costs 0.75 ALU op per weight.
+//
+// Fragment construction without a transpose: one AWQ word = 8 columns of ONE k, low half-word = even
+// columns, high half-word = odd columns.  For two consecutive rows (k, k+1) of the same word column
+//     lo = PRMT(w_k, w_k+1, 0x5410)   = [even cols of k | even cols of k+1]
+//     hi = PRMT(w_k, w_k+1, 0x7632)   = [odd  cols of k | odd  cols of k+1]
+// and  (lo >> 4t') & 0x000f000f | 0x64006400  is the fp16 pair (col 2t' @ k, col 2t' @ k+1) = 1024 + q,
+// i.e. a pair ALONG K, which is what the A fragment wants.  Nibbles sitting 4 bits higher are read with
+// mask 0x00f000f0 as 1024 + 16 q (kind B).  No per-weight zero/scale work at all: the tensor core
+// accumulates S = sum_k x_k * (1024 + c*q_k) in fp32 and the epilogue folds, per (group, column),
+//     y += s * ( S - (1024 + c*z) * sum_k x_k ) / c ,     c = 1 (kind A) or 16 (kind B).
+// The 1024 offset costs ~10 bits of the fp32 accumulator's 24: the result keeps >= 13 bits, above fp16.
+//
+// Warp tile = 256 columns x 16 rows: lane (g = lane/4, tig = lane%4) loads uint4 (4 words, 32 columns) at
+// word column 4g for rows 4 tig .. 4 tig + 3 (128 B contiguous per row across the 8 g's).  MMA (w, t)
+// takes A rows {g: column 8w+2t, g+8: column 8w+2t+1} of the lane's word w, A cols {2tig,2tig+1: rows
+// 0,1 of the lane; 2tig+8,+9: rows 2,3}; B = activations x[token g][those rows]; D row g / g+8, cols =
+// tokens 2tig, 2tig+1.  All M <= 8 tokens ride along for free.
+// CTA = NWARP warps sharing the column block, each walking its own k16-blocks; KC rows per CTA
+// (grid.y = K / KC slices, fp32 atomics into the zeroed workspace, last CTA rounds + re-zeroes).
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
-template <int WPT, int MT, int TX, int TY, int RPT>
-__global__ void __launch_bounds__(TX* TY)
+constexpr int kGvTN = 256;   // columns per CTA (one warp width)
+constexpr int kGvXPad = 8;   // halves of padding per token row of the staged activations
+
+// Warp `w` of a CTA owns the contiguous rows [k0 + w*RW, k0 + (w+1)*RW), RW = KC / NWARP (multiple of 16,
+// and a multiple or a divisor of G), i.e. gpw = max(1, RW / G) quantisation groups.
+template <int NWARP, int MT>
+__global__ void __launch_bounds__(NWARP * 32)
     gemv_gemm_layout_kernel(const __half* __restrict__ x, int64_t ldx, const int32_t* __restrict__ qweight,
                             const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                             const __half* __restrict__ bias, __half* __restrict__ y, float* __restrict__ acc_ws,
-                            int* __restrict__ tickets, int M, int K, int N, int G) {
-  constexpr int NT = TX * TY;
-  constexpr int CPT = 8 * WPT;        // columns per thread
-  constexpr int TN = CPT * TX;        // columns per CTA
-  constexpr int KC = RPT * TY;        // rows per CTA
-  constexpr int RB = (RPT < 8) ? RPT : 8;  // rows per load batch
-  static_assert(RPT % RB == 0, "RPT must be a multiple of the row batch");
-  static_assert(RPT % 2 == 0, "x is read as half2");
-
-  __shared__ __align__(16) __half xs[MT][KC];
-  __shared__ float xsum[MT][TY];           // per (token, ty): sum of x over that thread-row's RPT rows
-  __shared__ float red[TY][MT][TN + 4];    // +4 floats: de-phase the banks of consecutive ty
+                            int* __restrict__ tickets, int M, int K, int N, int G, int KC) {
+  extern __shared__ __align__(16) uint8_t gv_smem[];
+  // layout: xs [8][KC + pad] halves | xsum [NWARP][gpw][MT] floats | red [NWARP][gpw][MT][256] floats
+  const int xs_stride = KC + kGvXPad;
+  const int RW = KC / NWARP;
+  const int gpw = RW >= G ? RW / G : 1;
+  __half* xs = reinterpret_cast<__half*>(gv_smem);
+  float* xsum = reinterpret_cast<float*>(gv_smem + ((8 * xs_stride * 2 + 15) & ~15));
+  float* red = xsum + ((NWARP * gpw * MT + 3) & ~3);
   __shared__ int s_last;
 
-  const int tid = threadIdx.x;
-  const int tx = tid % TX, ty = tid / TX;
-  const int NW = N >> 3;                          // words per row
-  const int k0 = blockIdx.y * KC;                 // first row of this CTA
-  const int wc0 = blockIdx.x * (TN / 8) + tx * WPT;  // first word column of this thread
-  const bool col_ok = wc0 < NW;                   // N % (8*WPT) == 0 is guaranteed by the launcher
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tig = lane & 3;
+  const int NW = N >> 3;
+  const int k0 = blockIdx.y * KC;
+  const int n_base = blockIdx.x * kGvTN;
+  const int wc = (n_base >> 3) + 4 * g;        // first word column of this lane
+  const bool col_ok = wc < NW;                 // launcher guarantees N % 32 == 0 on this path
 
-  // ---- prologue: activations slice -> smem (zero padded past K / past M) ----------------------------
-  for (int i = tid; i < MT * KC; i += NT) {
-    const int m = i / KC, kk = i % KC;
+  // ---- prologue: stage x (tokens >= M and rows >= K are zero) ---------------------------------------
+  for (int i = tid; i < 8 * xs_stride; i += NWARP * 32) {
+    const int m = i / xs_stride, kk = i % xs_stride;
     __half v = __float2half(0.f);
-    if (m < M && k0 + kk < K) v = x[(int64_t)m * ldx + k0 + kk];
-    xs[m][kk] = v;
+    if (m < M && kk < KC && k0 + kk < K) v = x[(int64_t)m * ldx + k0 + kk];
+    xs[i] = v;
   }
   __syncthreads();
-  if (tid < MT * TY) {
-    const int m = tid / TY, t = tid % TY;
+  // per (warp, local group, token): sum of x over that warp's rows in that group
+  for (int i = tid; i < NWARP * gpw * MT; i += NWARP * 32) {
+    const int m = i % MT, gl = (i / MT) % gpw, w = i / (MT * gpw);
+    const int lo = w * RW + gl * G;
+    const int hi = lo + (RW >= G ? G : RW);
     float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < RPT; ++i) s += __half2float(xs[m][t * RPT + i]);
-    xsum[m][t] = s;
+    for (int kk = lo; kk < hi; ++kk) s += __half2float(xs[m * xs_stride + kk]);
+    xsum[i] = s;
   }
 
-  // ---- main loop: raw accumulation ------------------------------------------------------------------
-  float acc[MT][CPT];
+  // ---- main loop ------------------------------------------------------------------------------------
+  float acc[4][4][4];  // [word][t][d-reg]
+  auto zero_acc = [&]() {
 #pragma unroll
-  for (int m = 0; m < MT; ++m)
+    for (int w = 0; w < 4; ++w)
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[m][c] = 0.f;
-
-  const int r0 = k0 + ty * RPT;
-  const int32_t* wp = qweight + (int64_t)r0 * NW + wc0;
+      for (int t = 0; t < 4; ++t)
 #pragma unroll
-  for (int b = 0; b < RPT / RB; ++b) {
-    uint32_t q[RB][WPT];
+        for (int r = 0; r < 4; ++r) acc[w][t][r] = 0.f;
+  };
+  // D regs: d0/d1 = row g (column 8w+2t) tokens 2tig, 2tig+1 ; d2/d3 = row g+8 (column 8w+2t+1)
+  auto flush = [&](int gl) {
+    float* dst = red + (size_t)((warp * gpw + gl) * MT) * kGvTN;
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
-      const int r = r0 + b * RB + i;
-      if (col_ok && r < K) {
-        WordVec<WPT>::load(wp + (int64_t)(b * RB + i) * NW, q[i]);
-      } else {
+    for (int w = 0; w < 4; ++w)
 #pragma unroll
-        for (int w = 0; w < WPT; ++w) q[i][w] = 0u;
+      for (int t = 0; t < 4; ++t) {
+        const int c = 32 * g + 8 * w + 2 * t;
+        if (2 * tig < MT)
+          *reinterpret_cast<float2*>(&dst[(2 * tig) * kGvTN + c]) = make_float2(acc[w][t][0], acc[w][t][2]);
+        if (2 * tig + 1 < MT)
+          *reinterpret_cast<float2*>(&dst[(2 * tig + 1) * kGvTN + c]) = make_float2(acc[w][t][1], acc[w][t][3]);
       }
-    }
-    // activations of these RB rows for every token: RB halves = RB/2 words each
-    uint32_t xr[MT][RB / 2];
+  };
+  const int wrow0 = warp * RW;                 // first local row of this warp
+  const int blocks_per_grp = (RW >= G ? G : RW) / 16;
+  constexpr int UN = 2;                        // k16-blocks in flight
+  for (int gl = 0; gl < gpw; ++gl) {
+    zero_acc();
+    for (int b0 = 0; b0 < blocks_per_grp; b0 += UN) {
+      uint4 q[UN][4];
 #pragma unroll
-    for (int m = 0; m < MT; ++m)
+      for (int u = 0; u < UN; ++u) {
+        const int kl = wrow0 + gl * G + 16 * (b0 + u) + 4 * tig;  // local row
 #pragma unroll
-      for (int i = 0; i < RB / 2; ++i)
-        xr[m][i] = *reinterpret_cast<const uint32_t*>(&xs[m][ty * RPT + b * RB + 2 * i]);
+        for (int r = 0; r < 4; ++r) {
+          q[u][r] = make_uint4(0, 0, 0, 0);
+          if (col_ok && (b0 + u) < blocks_per_grp && k0 + kl + r < K)
+            q[u][r] = ldg_stream_u4(qweight + (int64_t)(k0 + kl + r) * NW + wc);
+        }
+      }
 #pragma unroll
-    for (int i = 0; i < RB; ++i) {
+      for (int u = 0; u < UN; ++u) {
+        if (b0 + u < blocks_per_grp) {
+          const int kl = wrow0 + gl * G + 16 * (b0 + u);
+          // B fragment: x[token g][rows 4tig .. 4tig+3 of this block]
+          const uint2 xb = *reinterpret_cast<const uint2*>(&xs[g * xs_stride + kl + 4 * tig]);
 #pragma unroll
-      for (int w = 0; w < WPT; ++w) {
-        const uint32_t word = q[i][w];
-        const uint32_t w8 = word >> 8;
-        const uint32_t p0 = word & 0x000f000fu, p1 = word & 0x00f000f0u;
-        const uint32_t p2 = w8 & 0x000f000fu, p3 = w8 & 0x00f000f0u;
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-          const uint16_t xh = (i & 1) ? hi16(xr[m][i / 2]) : lo16(xr[m][i / 2]);
-          float* a = &acc[m][w * 8];
-          a[0] = fhfma(lo16(p0), xh, a[0]);
-          a[1] = fhfma(hi16(p0), xh, a[1]);
-          a[2] = fhfma(lo16(p1), xh, a[2]);
-          a[3] = fhfma(hi16(p1), xh, a[3]);
-          a[4] = fhfma(lo16(p2), xh, a[4]);
-          a[5] = fhfma(hi16(p2), xh, a[5]);
-          a[6] = fhfma(lo16(p3), xh, a[6]);
-          a[7] = fhfma(hi16(p3), xh, a[7]);
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t wa = (&q[u][0].x)[w], wb = (&q[u][1].x)[w], wc_ = (&q[u][2].x)[w], wd = (&q[u][3].x)[w];
+            const uint32_t lo01 = __byte_perm(wa, wb, 0x5410), hi01 = __byte_perm(wa, wb, 0x7632);
+            const uint32_t lo23 = __byte_perm(wc_, wd, 0x5410), hi23 = __byte_perm(wc_, wd, 0x7632);
+            const uint32_t lo01s = lo01 >> 8, hi01s = hi01 >> 8, lo23s = lo23 >> 8, hi23s = hi23 >> 8;
+            constexpr uint32_t MA = 0x000f000fu, MB = 0x00f000f0u, MG = 0x64006400u;
+            // t = 0: columns 0,1 (kind A) ; t = 1: columns 2,3 (kind B) ; t = 2: columns 4,5 (A) ; t = 3: 6,7 (B)
+            mma_16816(acc[w][0], lop3_and_or(lo01, MA, MG), lop3_and_or(hi01, MA, MG), lop3_and_or(lo23, MA, MG),
+                      lop3_and_or(hi23, MA, MG), xb.x, xb.y);
+            mma_16816(acc[w][1], lop3_and_or(lo01, MB, MG), lop3_and_or(hi01, MB, MG), lop3_and_or(lo23, MB, MG),
+                      lop3_and_or(hi23, MB, MG), xb.x, xb.y);
+            mma_16816(acc[w][2], lop3_and_or(lo01s, MA, MG), lop3_and_or(hi01s, MA, MG), lop3_and_or(lo23s, MA, MG),
+                      lop3_and_or(hi23s, MA, MG), xb.x, xb.y);
+            mma_16816(acc[w][3], lop3_and_or(lo01s, MB, MG), lop3_and_or(hi01s, MB, MG), lop3_and_or(lo23s, MB, MG),
+                      lop3_and_or(hi23s, MB, MG), xb.x, xb.y);
+          }
         }
       }
     }
+    flush(gl);
   }
-
-  // ---- cross-thread reduction over ty through smem --------------------------------------------------
-#pragma unroll
-  for (int m = 0; m < MT; ++m)
-#pragma unroll
-    for (int c = 0; c < CPT; c += 4)
-      *reinterpret_cast<float4*>(&red[ty][m][tx * CPT + c]) =
-          make_float4(acc[m][c], acc[m][c + 1], acc[m][c + 2], acc[m][c + 3]);
   __syncthreads();
 
-  // ---- fold scale / zero-point per (group, column), write or accumulate ----------------------------
-  const int n_base = blockIdx.x * TN;
+  // ---- fold zero-point / scale per (warp-slice, group, column); one thread per output ---------------
   const bool split = gridDim.y > 1;
-  for (int o = tid; o < MT * TN; o += NT) {
-    const int m = o / TN, c = o % TN;
+  for (int o = tid; o < MT * kGvTN; o += NWARP * 32) {
+    const int m = o / kGvTN, c = o % kGvTN;
     const int n = n_base + c;
     if (m >= M || n >= N) continue;
-    const int j = c & 7;                       // column inside its word
-    const float cs = ((j >> 1) & 1) ? kScaleB : kScaleA;
-    const int zshift = 4 * ((j >> 1) + 4 * (j & 1));  // AWQ_REVERSE_ORDER[j] * 4
+    const int j = c & 7;
+    const bool kindB = ((j >> 1) & 1) != 0;
+    const int zshift = 4 * ((j >> 1) + 4 * (j & 1));  // 4 * AWQ_REVERSE_ORDER[j]
     float val = 0.f;
-    // thread-rows are grouped by quantisation group: ty -> (k0 + ty*RPT) / G
-    int t = 0;
-    while (t < TY) {
-      const int krow = k0 + t * RPT;
-      if (krow >= K) break;
-      const int g = krow / G;
-      float raw = 0.f, xsg = 0.f;
-      // consecutive thread-rows in the same group
-      while (t < TY && (k0 + t * RPT) < K && (k0 + t * RPT) / G == g) {
-        raw += red[t][m][c];
-        xsg += xsum[m][t];
-        ++t;
+    int last_g = -1;
+    float s = 0.f, zoff = 0.f;
+    for (int w = 0; w < NWARP; ++w) {
+      for (int gl = 0; gl < gpw; ++gl) {
+        const int krow = k0 + w * RW + gl * G;
+        if (krow >= K) break;
+        const int gabs = krow / G;
+        if (gabs != last_g) {
+          last_g = gabs;
+          s = __half2float(scales[(int64_t)gabs * N + n]);
+          const float z =
+              static_cast<float>((static_cast<uint32_t>(qzeros[(int64_t)gabs * NW + (n >> 3)]) >> zshift) & 0xFu);
+          zoff = kindB ? 1024.f + 16.f * z : 1024.f + z;
+          if (kindB) s *= 0.0625f;
+        }
+        const float S = red[(size_t)((w * gpw + gl) * MT + m) * kGvTN + c];
+        val += s * (S - zoff * xsum[(w * gpw + gl) * MT + m]);
       }
-      const float s = __half2float(scales[(int64_t)g * N + n]);
-      const float z = static_cast<float>((static_cast<uint32_t>(qzeros[(int64_t)g * NW + (n >> 3)]) >> zshift) & 0xFu);
-      val += s * (cs * raw - z * xsg);
     }
     if (!split) {
       if (bias != nullptr) val += __half2float(bias[n]);
@@ -194,8 +214,8 @@ __global__ void __launch_bounds__(TX* TY)
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int o = tid; o < MT * TN; o += NT) {
-    const int m = o / TN, c = o % TN;
+  for (int o = tid; o < MT * kGvTN; o += NWARP * 32) {
+    const int m = o / kGvTN, c = o % kGvTN;
     const int n = n_base + c;
     if (m >= M || n >= N) continue;
     float* p = &acc_ws[(int64_t)m * N + n];
@@ -207,39 +227,57 @@ __global__ void __launch_bounds__(TX* TY)
   if (tid == 0) tickets[blockIdx.x] = 0;
 }
 
-template <int WPT, int MT, int TX, int TY, int RPT>
-static cudaError_t launch_gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st) {
-  constexpr int TN = 8 * WPT * TX, KC = RPT * TY;
-  dim3 grid((a.N + TN - 1) / TN, (a.K + KC - 1) / KC);
-  gemv_gemm_layout_kernel<WPT, MT, TX, TY, RPT><<<grid, TX * TY, 0, st>>>(
-      reinterpret_cast<const __half*>(a.x), a.ldx, a.qweight, reinterpret_cast<const __half*>(a.scales), a.qzeros,
-      reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M, a.K, a.N, a.G);
+template <int NWARP, int MT>
+static cudaError_t launch_gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, int KC, cudaStream_t st) {
+  const int RW = KC / NWARP;
+  const int gpw = RW >= a.G ? RW / a.G : 1;
+  const int xs_bytes = (8 * (KC + kGvXPad) * 2 + 15) & ~15;
+  const size_t smem = (size_t)xs_bytes + (size_t)((NWARP * gpw * MT + 3) & ~3) * 4 + (size_t)NWARP * gpw * MT * kGvTN * 4;
+  auto kern = gemv_gemm_layout_kernel<NWARP, MT>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((a.N + kGvTN - 1) / kGvTN, (a.K + KC - 1) / KC);
+  kern<<<grid, NWARP * 32, smem, st>>>(reinterpret_cast<const __half*>(a.x), a.ldx, a.qweight,
+                                       reinterpret_cast<const __half*>(a.scales), a.qzeros,
+                                       reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y),
+                                       acc_ws, tickets, a.M, a.K, a.N, a.G, KC);
   return cudaGetLastError();
 }
 
-// Thread-rows must not straddle a quantisation group: RPT | G.  G is a multiple of 32 in every AWQ
-// checkpoint (32 / 64 / 128 / K); the launcher falls back to RPT = 2 for exotic group sizes.
+// Rows per CTA (KC): NWARP * RW with RW (rows per warp) a multiple of 16 that is a multiple or a divisor of
+// G; sized so the grid has a few CTAs per SM (148 SMs) without starving each CTA of work.
+static int pick_kc(int K, int N, int G, int nwarp, int mt) {
+  int rw;  // rows per warp
+  const int forced = knob(0);
+  if (forced > 0) {
+    rw = forced / nwarp;
+  } else {
+    const int colblk = (N + kGvTN - 1) / kGvTN;
+    rw = 32;
+    while (rw < 512 && (int64_t)colblk * ((K + rw * nwarp - 1) / (rw * nwarp)) > 148 * 6) rw *= 2;
+  }
+  if (rw < 16) rw = 16;
+  if (rw >= G) rw = rw / G * G; else while (G % rw != 0) rw /= 2;
+  // bound the per-warp reduction buffer: gpw * MT <= 8
+  while (rw > G && (rw / G) * mt > 8) rw -= G;
+  return rw * nwarp;
+}
+
+// N % 32 == 0 and G % 16 == 0 (every AWQ checkpoint: G in {32, 64, 128, K}) take the tensor-pipe GEMV;
+// other shapes are routed to the tcgen05 kernel by the C-ABI layer (token tile padded by TMA zero fill).
+bool gemv_gemm_layout_supported(const GemmArgs& a) {
+  return (a.N % 32) == 0 && (a.G % 16) == 0 && (reinterpret_cast<uintptr_t>(a.qweight) % 16) == 0 && a.M <= 8;
+}
+
 cudaError_t gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st) {
-  const bool vec4 = (a.N % 32) == 0 && (reinterpret_cast<uintptr_t>(a.qweight) % 16) == 0;
-  const bool rpt16 = (a.G % 16) == 0;
-  if (!rpt16) {
-    // generic slow-but-correct shape: one word per thread, 2 rows per thread
-    if (a.M <= 1) return launch_gemv_gemm_layout<1, 1, 32, 4, 2>(a, acc_ws, tickets, st);
-    if (a.M <= 2) return launch_gemv_gemm_layout<1, 2, 32, 4, 2>(a, acc_ws, tickets, st);
-    if (a.M <= 4) return launch_gemv_gemm_layout<1, 4, 32, 4, 2>(a, acc_ws, tickets, st);
-    return launch_gemv_gemm_layout<1, 8, 32, 4, 2>(a, acc_ws, tickets, st);
-  }
-  if (a.M <= 1) {
-    if (vec4) return launch_gemv_gemm_layout<4, 1, 16, 8, 16>(a, acc_ws, tickets, st);
-    return launch_gemv_gemm_layout<1, 1, 32, 4, 16>(a, acc_ws, tickets, st);
-  }
-  const bool vec2 = (a.N % 16) == 0 && (reinterpret_cast<uintptr_t>(a.qweight) % 8) == 0;
-  if (a.M <= 2) {
-    if (vec2) return launch_gemv_gemm_layout<2, 2, 16, 8, 16>(a, acc_ws, tickets, st);
-    return launch_gemv_gemm_layout<1, 2, 32, 4, 16>(a, acc_ws, tickets, st);
-  }
-  if (a.M <= 4) return launch_gemv_gemm_layout<1, 4, 32, 4, 16>(a, acc_ws, tickets, st);
-  return launch_gemv_gemm_layout<1, 8, 32, 4, 16>(a, acc_ws, tickets, st);
+  const int mt = a.M <= 1 ? 1 : (a.M <= 2 ? 2 : (a.M <= 4 ? 4 : 8));
+  const int KC = pick_kc(a.K, a.N, a.G, 4, mt);
+  if (mt == 1) return launch_gemv_gemm_layout<4, 1>(a, acc_ws, tickets, KC, st);
+  if (mt == 2) return launch_gemv_gemm_layout<4, 2>(a, acc_ws, tickets, KC, st);
+  if (mt == 4) return launch_gemv_gemm_layout<4, 4>(a, acc_ws, tickets, KC, st);
+  return launch_gemv_gemm_layout<4, 8>(a, acc_ws, tickets, KC, st);
 }
 
 }  // namespace b200awq

@@ -38,6 +38,7 @@ int knob(int key);
 cudaError_t dequantize_gemm(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out, int K,
                             int N, int G, cudaStream_t st);
 
+bool gemv_gemm_layout_supported(const GemmArgs& a);
 cudaError_t gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st);
 cudaError_t gemv_gemv_layout(const GemmArgs& a, cudaStream_t st);
 cudaError_t gemv_fast_layout(const FastArgs& a, cudaStream_t st);

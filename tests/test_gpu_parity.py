@@ -2,11 +2,16 @@
 operator surface and the WQLinear_* mirrors (both sit on the C ABI of libb200awq.so), against the CPU
 oracle on the same seeded inputs and against the golden vectors produced by the real reference.
 
-Bars: integer unpack + dequantisation: BIT-EXACT.  Forward outputs (fp16): within
-    |y - y64| <= 2^-10 * |y64| + 1e-3 * rms(y64)
-of the fp64 contraction of the bit-exact dequantised weights (one fp16 rounding is 2^-11 relative; the
-second term covers fp32 accumulation over K <= 14336 under cancellation).  The reference itself pins no
-GEMM/GEMV output; its only GEMM-level tolerance anywhere is rtol 6e-2 (tests/test_ipex_cpu.py:59).
+Bars: integer unpack + dequantisation: BIT-EXACT.  Forward outputs (fp16), against the fp64 contraction
+y64 = X . W16 of the bit-exact dequantised fp16 weights:
+    |y - y64| <= 2^-10 * |y64|  +  wr * (|X| . |W16|)  +  1e-6
+  * 2^-10 |y64|: the single rounding of the result to fp16 (2^-11) with a factor 2 of slack;
+  * wr = 2^-16 on the tcgen05 path (its A operand IS W16, bit-exact; only fp32 accumulation order differs);
+  * wr = 2^-11 on the M <= 8 GEMV path: it applies scale / zero-point per group in fp32 instead of rounding
+    every weight to fp16 first - closer to the real-number value (q - z) * s than the reference, and at most
+    one fp16 rounding PER WEIGHT away from it, which is exactly what 2^-11 (|X| . |W16|) bounds.
+The reference itself pins no GEMM/GEMV output; its only GEMM-level tolerance anywhere is
+rtol 6e-2 (tests/test_ipex_cpu.py:59).
 """
 import hashlib
 import os
@@ -20,7 +25,8 @@ from oracle import awq_oracle as O
 pytestmark = pytest.mark.gpu
 
 RTOL = 2.0**-10
-ATOL_RMS = 1e-3
+WR_GEMV = 2.0**-11
+WR_TC = 2.0**-16
 
 
 def _bits(a):
@@ -35,9 +41,13 @@ def _t(a):
     return torch.from_numpy(np.ascontiguousarray(a)).to(_dev())
 
 
-def _close(y, ref64, what=""):
+def _budget(x, w):
+    return np.abs(np.asarray(x, dtype=np.float64)) @ np.abs(np.asarray(w, dtype=np.float64))
+
+
+def _close(y, ref64, budget, wr, what=""):
     y = np.asarray(y, dtype=np.float64)
-    tol = RTOL * np.abs(ref64) + ATOL_RMS * np.sqrt(np.mean(ref64**2)) + 1e-7
+    tol = RTOL * np.abs(ref64) + wr * budget + 1e-6
     bad = np.abs(y - ref64) > tol
     assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} outside tolerance, max err {np.abs(y - ref64).max():.3e}"
 
@@ -109,7 +119,7 @@ def _forward_case(ext, K, N, G, raw, Ms, seed=0, bias=True):
         y = ext.linear_forward("gemm", _t(x), qw, sc, qz, Gs, bt).cpu().numpy()
         ref = O.gemm_f64(x, w) + (b.astype(np.float64) if bias else 0.0)
         assert y.shape == (M, N) and y.dtype == np.float16
-        _close(y, ref, f"gemm layout K={K} N={N} G={Gs} M={M}")
+        _close(y, ref, _budget(x, w), WR_GEMV if M <= 8 else WR_TC, f"gemm layout K={K} N={N} G={Gs} M={M}")
 
 
 @pytest.mark.parametrize("K,N,G,raw", CASES)
@@ -131,7 +141,7 @@ def test_forward_prefill_full_size(ext):
     x = rng.standard_normal((4096, K)).astype(np.float16)
     y = ext.linear_forward("gemm", _t(x), _t(c["qweight"]), _t(c["scales"]), _t(c["qzeros"]), 128).cpu().numpy()
     rows = np.array([0, 1, 255, 256, 1000, 2047, 2048, 4095])
-    _close(y[rows], O.gemm_f64(x[rows], w), "prefill 4096^3")
+    _close(y[rows], O.gemm_f64(x[rows], w), _budget(x[rows], w), WR_TC, "prefill 4096^3")
 
 
 def test_one_hot_rows_reproduce_dequant_bit_exact(ext):
@@ -254,10 +264,10 @@ def test_three_layouts_agree(ext, K, N, G):
         else:
             yv = awq_ext.gemv_forward_cuda(_t(x), _t(vw), _t(vs), _t(vz), G)
             yf = awq_v2_ext.gemv_forward_cuda_decode(_t(x).unsqueeze(1), _t(fw), _t(fs), _t(fz), M, N, K, G)[:, 0]
-        _close(yv.cpu().numpy(), ref, f"gemv layout M={M}")
+        _close(yv.cpu().numpy(), ref, _budget(x, w), WR_GEMV if M <= 8 else WR_TC, f"gemv layout M={M}")
         # GEMVFast stores -(z*s) rounded to fp16: its exact value is q*s + sz (oracle), which differs from
         # (q-z)*s by that rounding; compare against its own fp64 truth
-        _close(yf.cpu().numpy(), O.gemm_f64(x, wfast), f"fast layout M={M}")
+        _close(yf.cpu().numpy(), O.gemm_f64(x, wfast), _budget(x, wfast), WR_GEMV, f"fast layout M={M}")
 
 
 def test_gemv_module_mirrors(ext):
@@ -274,9 +284,11 @@ def test_gemv_module_mirrors(ext):
     mf.qweight.copy_(_t(fw)); mf.qzeros.copy_(_t(fz)); mf.scales.copy_(_t(fs))
     x = np.random.default_rng(0).standard_normal((2, 1, K)).astype(np.float16)
     ref = O.gemm_f64(x.reshape(-1, K), w).reshape(2, 1, N)
-    _close(mv(_t(x)).cpu().numpy(), ref, "WQLinear_GEMV")
-    _close(mf(_t(x)).cpu().numpy(), O.gemm_f64(x.reshape(-1, K), O.dequantize_gemv_fast_f64(fw, fs, fz, G)).reshape(2, 1, N),
-           "WQLinear_GEMVFast")
+    bud = _budget(x.reshape(-1, K), w).reshape(2, 1, N)
+    _close(mv(_t(x)).cpu().numpy(), ref, bud, WR_GEMV, "WQLinear_GEMV")
+    wf = O.dequantize_gemv_fast_f64(fw, fs, fz, G)
+    _close(mf(_t(x)).cpu().numpy(), O.gemm_f64(x.reshape(-1, K), wf).reshape(2, 1, N),
+           _budget(x.reshape(-1, K), wf).reshape(2, 1, N), WR_GEMV, "WQLinear_GEMVFast")
 
 
 # ---------------------------------------------------------------------------------- glue kernels

@@ -41,7 +41,7 @@ def check_paths():
         x = rng.standard_normal((M, K)).astype(np.float16)
         y = ext.linear_forward("gemm", t(x), t(c["qweight"]), t(c["scales"]), t(c["qzeros"]), G).cpu().numpy()
         res[f"gemv_M{M}_relerr"] = relerr(y, O.gemm_f64(x, w))
-    for variant in (0, 1):
+    for variant in (0,):
         ext.set_knob(3, variant)
         for M in (16, 100, 256):
             x = rng.standard_normal((M, K)).astype(np.float16)
@@ -65,16 +65,30 @@ def check_paths():
 
 
 def time_kernel(fn, nbuf, iters=200, warm=20):
-    for i in range(warm):
-        fn(i % nbuf)
+    """Device time per call: the nbuf calls (rotating weight buffers, pool > L2) are captured into ONE CUDA
+    graph so that Python / ctypes launch overhead (~15 us per call) is not what gets measured."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(min(nbuf, 3)):
+            fn(i)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for i in range(nbuf):
+            fn(i)
+    reps = max(1, iters // nbuf)
+    for _ in range(max(1, warm // nbuf)):
+        g.replay()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for i in range(iters):
-        fn(i % nbuf)
+    for _ in range(reps):
+        g.replay()
     e.record()
     torch.cuda.synchronize()
-    return s.elapsed_time(e) / iters * 1e3  # us
+    return s.elapsed_time(e) / (reps * nbuf) * 1e3  # us
 
 
 def bench_shapes():
@@ -83,7 +97,7 @@ def bench_shapes():
     shapes = [(4096, 4096), (4096, 6144), (4096, 14336), (14336, 4096), (4096, 28672)]
     for (K, N) in shapes:
         wbytes = K * N // 2 + (K // G) * N * 2 + (K // G) * N // 2
-        nbuf = max(2, int(300e6 // wbytes) + 1)
+        nbuf = max(3, int(400e6 // wbytes) + 1)
         qw = [torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
         qz = [torch.randint(-2**31, 2**31 - 1, (K // G, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
         sc = [(torch.rand((K // G, N), device=dev) * 0.01 + 0.001).half() for _ in range(nbuf)]

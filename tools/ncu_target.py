@@ -1,0 +1,27 @@
+"""Small launch sequences for ncu captures (run under `ncu ... python tools/ncu_target.py <what>`).
+what = gemv : 4096x4096 g128 M=1 GEMV over a rotating 400 MB weight pool (DRAM-resident)
+       gemv_big : 4096x28672 M=1
+       gemm : 4096x4096x4096 tcgen05 GEMM
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from autoawq_b200 import ext  # noqa: E402
+
+dev = torch.device("cuda:0")
+what = sys.argv[1] if len(sys.argv) > 1 else "gemv"
+K, N, M = {"gemv": (4096, 4096, 1), "gemv_big": (4096, 28672, 1), "gemm": (4096, 4096, 4096),
+           "gemm64": (4096, 14336, 64)}[what]
+G = 128
+wbytes = K * N // 2
+nbuf = max(3, int(400e6 // wbytes) + 1)
+qw = [torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
+qz = [torch.randint(-2**31, 2**31 - 1, (K // G, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
+sc = [(torch.rand((K // G, N), device=dev) * 0.01 + 0.001).half() for _ in range(nbuf)]
+x = torch.randn((M, K), device=dev, dtype=torch.float16)
+for i in range(2 * nbuf):
+    ext.linear_forward("gemm", x, qw[i % nbuf], sc[i % nbuf], qz[i % nbuf], G)
+torch.cuda.synchronize()
