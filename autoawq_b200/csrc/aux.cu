@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256)
     rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ out, int hidden,
                    float eps) {
   __shared__ float wsum[8];
+  pdl_trigger();
+  pdl_wait();
   const __half* xr = x + (int64_t)blockIdx.x * hidden;
   __half* orow = out + (int64_t)blockIdx.x * hidden;
   float ss = 0.f;
@@ -53,6 +55,8 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     silu_mul_kernel(const __half* __restrict__ gu, __half* __restrict__ out, int rows, int d) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)rows * d) return;
   const int r = static_cast<int>(i / d), j = static_cast<int>(i % d);
@@ -62,15 +66,13 @@ __global__ void __launch_bounds__(256)
 }
 
 cudaError_t rmsnorm(const void* x, const void* w, void* out, int rows, int hidden, float eps, cudaStream_t st) {
-  rmsnorm_kernel<<<rows, 256, 0, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(w),
-                                       reinterpret_cast<__half*>(out), hidden, eps);
-  return cudaGetLastError();
+  return launch_kernel(rmsnorm_kernel, dim3(rows), dim3(256), 0, st, reinterpret_cast<const __half*>(x),
+                       reinterpret_cast<const __half*>(w), reinterpret_cast<__half*>(out), hidden, eps);
 }
 cudaError_t silu_and_mul(const void* gate_up, void* out, int rows, int d, cudaStream_t st) {
   const int64_t n = (int64_t)rows * d;
-  silu_mul_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(gate_up),
-                                                                     reinterpret_cast<__half*>(out), rows, d);
-  return cudaGetLastError();
+  return launch_kernel(silu_mul_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st,
+                       reinterpret_cast<const __half*>(gate_up), reinterpret_cast<__half*>(out), rows, d);
 }
 
 }  // namespace b200awq

@@ -56,6 +56,15 @@ __device__ __forceinline__ float ldcg_f1(const void* p) {
   return r;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor is still running.  pdl_trigger() lets OUR successor start
+// early; pdl_wait() blocks until the predecessor grid has completed and its writes are visible - it must
+// precede every access to memory the predecessor may write (activations, workspace, outputs).  Loads of
+// the packed weights (never written on the stream) are issued BEFORE pdl_wait(): consecutive linears
+// then stream weights back to back.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------- int4 -> fp16 unpack
 // (a & b) | c in one LOP3
 __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t b, uint32_t c) {

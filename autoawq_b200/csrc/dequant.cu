@@ -11,6 +11,8 @@ template <int WPT, int ROWS>
 __global__ void __launch_bounds__(256)
     dequant_gemm_kernel(const int32_t* __restrict__ qweight, const __half* __restrict__ scales,
                         const int32_t* __restrict__ qzeros, __half* __restrict__ out, int K, int N, int G) {
+  pdl_trigger();
+  pdl_wait();
   const int NW = N >> 3;
   const int nvec = NW / WPT;  // word-vectors per row
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,15 +66,11 @@ cudaError_t dequantize_gemm(const int32_t* qweight, const void* scales, const in
   const int blocks = static_cast<int>((threads + 255) / 256);
   const __half* s = reinterpret_cast<const __half*>(scales);
   __half* o = reinterpret_cast<__half*>(out);
-  if (vec && rows8)
-    dequant_gemm_kernel<4, 8><<<blocks, 256, 0, st>>>(qweight, s, qzeros, o, K, N, G);
-  else if (vec)
-    dequant_gemm_kernel<4, 1><<<blocks, 256, 0, st>>>(qweight, s, qzeros, o, K, N, G);
-  else if (rows8)
-    dequant_gemm_kernel<1, 8><<<blocks, 256, 0, st>>>(qweight, s, qzeros, o, K, N, G);
-  else
-    dequant_gemm_kernel<1, 1><<<blocks, 256, 0, st>>>(qweight, s, qzeros, o, K, N, G);
-  return cudaGetLastError();
+  const dim3 grid(blocks), block(256);
+  if (vec && rows8) return launch_kernel(dequant_gemm_kernel<4, 8>, grid, block, 0, st, qweight, s, qzeros, o, K, N, G);
+  if (vec) return launch_kernel(dequant_gemm_kernel<4, 1>, grid, block, 0, st, qweight, s, qzeros, o, K, N, G);
+  if (rows8) return launch_kernel(dequant_gemm_kernel<1, 8>, grid, block, 0, st, qweight, s, qzeros, o, K, N, G);
+  return launch_kernel(dequant_gemm_kernel<1, 1>, grid, block, 0, st, qweight, s, qzeros, o, K, N, G);
 }
 
 }  // namespace b200awq

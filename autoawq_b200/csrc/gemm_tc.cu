@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmx);
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 0) {
     // ================================================================= TMA producer (X tiles)
     if (lane == 0) {
+      pdl_wait();  // the activations are the predecessor's output
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -335,6 +337,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // ================================================================= epilogue (4 warps)
     const int et = threadIdx.x - 64;  // 0..127
     const int q4 = warp & 3;          // TMEM lane quadrant this warp may read
+    pdl_wait();                       // outputs / workspace may alias memory the predecessor still uses
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int mt = (w / p.ksplit) % p.m_tiles;
@@ -512,8 +515,7 @@ static cudaError_t launch_tc(const CUtensorMap& tm, const TcParams& p, cudaStrea
   }
   const int n_work = p.n_tiles * p.m_tiles * p.ksplit;
   const int grid = n_work < sm_count() ? n_work : sm_count();
-  kern<<<grid, kTcThreads, Cfg::kSmemBytes, st>>>(tm, p);
-  return cudaGetLastError();
+  return launch_kernel(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, st, tm, p);
 }
 
 template <int LAYOUT>

@@ -48,25 +48,28 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-constexpr int kGvTN = 256;   // columns per CTA (one warp width)
-constexpr int kGvXPad = 8;   // halves of padding per token row of the staged activations
+constexpr int kGvTN = 256;       // columns per CTA (one warp width)
+constexpr int kGvWarps = 8;      // warps per CTA, each on its own contiguous RW rows
+constexpr int kGvRedStride = kGvTN + 16;  // +2 floats per 32 columns: conflict-free float2 stores
 
-// Warp `w` of a CTA owns the contiguous rows [k0 + w*RW, k0 + (w+1)*RW), RW = KC / NWARP (multiple of 16,
-// and a multiple or a divisor of G), i.e. gpw = max(1, RW / G) quantisation groups.
-template <int NWARP, int MT>
-__global__ void __launch_bounds__(NWARP * 32)
+__device__ __forceinline__ int gv_pos(int c) { return c + ((c >> 5) << 1); }
+
+// Lean by construction - a 4096x4096 GEMV is ~59 KB per SM (~1 us of HBM time), so every prologue /
+// epilogue instruction shows: no shared-memory staging of x (B fragments come straight from global, issued
+// with the weight loads), sum_k x_k comes out of one extra MMA against an all-ones A fragment, no runtime
+// divisions, one __syncthreads.  RW (rows per warp, 32/64/128) divides G, so a warp's rows sit in ONE
+// quantisation group and its accumulators are folded once.
+template <int MT, int RW>
+__global__ void __launch_bounds__(kGvWarps * 32, 2)
     gemv_gemm_layout_kernel(const __half* __restrict__ x, int64_t ldx, const int32_t* __restrict__ qweight,
                             const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                             const __half* __restrict__ bias, __half* __restrict__ y, float* __restrict__ acc_ws,
-                            int* __restrict__ tickets, int M, int K, int N, int G, int KC) {
-  extern __shared__ __align__(16) uint8_t gv_smem[];
-  // layout: xs [8][KC + pad] halves | xsum [NWARP][gpw][MT] floats | red [NWARP][gpw][MT][256] floats
-  const int xs_stride = KC + kGvXPad;
-  const int RW = KC / NWARP;
-  const int gpw = RW >= G ? RW / G : 1;
-  __half* xs = reinterpret_cast<__half*>(gv_smem);
-  float* xsum = reinterpret_cast<float*>(gv_smem + ((8 * xs_stride * 2 + 15) & ~15));
-  float* red = xsum + ((NWARP * gpw * MT + 3) & ~3);
+                            int* __restrict__ tickets, int M, int K, int N, int G) {
+  constexpr int NB = RW / 16;                  // k16-blocks per warp
+  constexpr int KC = kGvWarps * RW;            // rows per CTA
+  extern __shared__ __align__(16) float gv_dyn[];
+  float (*red)[MT][kGvRedStride] = reinterpret_cast<float (*)[MT][kGvRedStride]>(gv_dyn);
+  float (*xsum_s)[MT] = reinterpret_cast<float (*)[MT]>(gv_dyn + kGvWarps * MT * kGvRedStride);
   __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -75,131 +78,141 @@ __global__ void __launch_bounds__(NWARP * 32)
   const int k0 = blockIdx.y * KC;
   const int n_base = blockIdx.x * kGvTN;
   const int wc = (n_base >> 3) + 4 * g;        // first word column of this lane
-  const bool col_ok = wc < NW;                 // launcher guarantees N % 32 == 0 on this path
+  const bool col_ok = wc < NW;                 // N % 32 == 0 on this path
+  const int wrow = k0 + warp * RW;             // first row of this warp
+  const bool tok_ok = g < M;                   // this lane feeds token g into the B fragment
 
-  // ---- prologue: stage x (tokens >= M and rows >= K are zero) ---------------------------------------
-  for (int i = tid; i < 8 * xs_stride; i += NWARP * 32) {
-    const int m = i / xs_stride, kk = i % xs_stride;
-    __half v = __float2half(0.f);
-    if (m < M && kk < KC && k0 + kk < K) v = x[(int64_t)m * ldx + k0 + kk];
-    xs[i] = v;
-  }
-  __syncthreads();
-  // per (warp, local group, token): sum of x over that warp's rows in that group
-  for (int i = tid; i < NWARP * gpw * MT; i += NWARP * 32) {
-    const int m = i % MT, gl = (i / MT) % gpw, w = i / (MT * gpw);
-    const int lo = w * RW + gl * G;
-    const int hi = lo + (RW >= G ? G : RW);
-    float s = 0.f;
-    for (int kk = lo; kk < hi; ++kk) s += __half2float(xs[m * xs_stride + kk]);
-    xsum[i] = s;
-  }
-
-  // ---- main loop ------------------------------------------------------------------------------------
-  float acc[4][4][4];  // [word][t][d-reg]
-  auto zero_acc = [&]() {
+  // ---- software pipeline: two k16-blocks of weights (+ activations) in flight per lane ---------------
+  uint4 q[2][4];
+  uint2 xb[2];
+  auto issue_w = [&](int slot, int b) {
+    const int kr = wrow + 16 * b + 4 * tig;    // this lane's 4 rows of block b
+    const int32_t* src = qweight + (int64_t)kr * NW + wc;
 #pragma unroll
-    for (int w = 0; w < 4; ++w)
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[w][t][r] = 0.f;
-  };
-  // D regs: d0/d1 = row g (column 8w+2t) tokens 2tig, 2tig+1 ; d2/d3 = row g+8 (column 8w+2t+1)
-  auto flush = [&](int gl) {
-    float* dst = red + (size_t)((warp * gpw + gl) * MT) * kGvTN;
-#pragma unroll
-    for (int w = 0; w < 4; ++w)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int c = 32 * g + 8 * w + 2 * t;
-        if (2 * tig < MT)
-          *reinterpret_cast<float2*>(&dst[(2 * tig) * kGvTN + c]) = make_float2(acc[w][t][0], acc[w][t][2]);
-        if (2 * tig + 1 < MT)
-          *reinterpret_cast<float2*>(&dst[(2 * tig + 1) * kGvTN + c]) = make_float2(acc[w][t][1], acc[w][t][3]);
-      }
-  };
-  const int wrow0 = warp * RW;                 // first local row of this warp
-  const int blocks_per_grp = (RW >= G ? G : RW) / 16;
-  constexpr int UN = 2;                        // k16-blocks in flight
-  for (int gl = 0; gl < gpw; ++gl) {
-    zero_acc();
-    for (int b0 = 0; b0 < blocks_per_grp; b0 += UN) {
-      uint4 q[UN][4];
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int kl = wrow0 + gl * G + 16 * (b0 + u) + 4 * tig;  // local row
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          q[u][r] = make_uint4(0, 0, 0, 0);
-          if (col_ok && (b0 + u) < blocks_per_grp && k0 + kl + r < K)
-            q[u][r] = ldg_stream_u4(qweight + (int64_t)(k0 + kl + r) * NW + wc);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        if (b0 + u < blocks_per_grp) {
-          const int kl = wrow0 + gl * G + 16 * (b0 + u);
-          // B fragment: x[token g][rows 4tig .. 4tig+3 of this block]
-          const uint2 xb = *reinterpret_cast<const uint2*>(&xs[g * xs_stride + kl + 4 * tig]);
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const uint32_t wa = (&q[u][0].x)[w], wb = (&q[u][1].x)[w], wc_ = (&q[u][2].x)[w], wd = (&q[u][3].x)[w];
-            const uint32_t lo01 = __byte_perm(wa, wb, 0x5410), hi01 = __byte_perm(wa, wb, 0x7632);
-            const uint32_t lo23 = __byte_perm(wc_, wd, 0x5410), hi23 = __byte_perm(wc_, wd, 0x7632);
-            const uint32_t lo01s = lo01 >> 8, hi01s = hi01 >> 8, lo23s = lo23 >> 8, hi23s = hi23 >> 8;
-            constexpr uint32_t MA = 0x000f000fu, MB = 0x00f000f0u, MG = 0x64006400u;
-            // t = 0: columns 0,1 (kind A) ; t = 1: columns 2,3 (kind B) ; t = 2: columns 4,5 (A) ; t = 3: 6,7 (B)
-            mma_16816(acc[w][0], lop3_and_or(lo01, MA, MG), lop3_and_or(hi01, MA, MG), lop3_and_or(lo23, MA, MG),
-                      lop3_and_or(hi23, MA, MG), xb.x, xb.y);
-            mma_16816(acc[w][1], lop3_and_or(lo01, MB, MG), lop3_and_or(hi01, MB, MG), lop3_and_or(lo23, MB, MG),
-                      lop3_and_or(hi23, MB, MG), xb.x, xb.y);
-            mma_16816(acc[w][2], lop3_and_or(lo01s, MA, MG), lop3_and_or(hi01s, MA, MG), lop3_and_or(lo23s, MA, MG),
-                      lop3_and_or(hi23s, MA, MG), xb.x, xb.y);
-            mma_16816(acc[w][3], lop3_and_or(lo01s, MB, MG), lop3_and_or(hi01s, MB, MG), lop3_and_or(lo23s, MB, MG),
-                      lop3_and_or(hi23s, MB, MG), xb.x, xb.y);
-          }
-        }
-      }
+    for (int r = 0; r < 4; ++r) {
+      q[slot][r] = make_uint4(0, 0, 0, 0);
+      if (col_ok && kr + r < K) q[slot][r] = ldg_stream_u4(src + (int64_t)r * NW);
     }
-    flush(gl);
+  };
+  auto issue_x = [&](int slot, int b) {
+    const int kr = wrow + 16 * b + 4 * tig;
+    xb[slot] = make_uint2(0, 0);
+    if (tok_ok && kr + 3 < K) {
+      xb[slot] = *reinterpret_cast<const uint2*>(x + (int64_t)g * ldx + kr);
+    } else if (tok_ok && kr < K) {             // ragged K tail
+      __half t[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) t[r] = (kr + r < K) ? x[(int64_t)g * ldx + kr + r] : __float2half(0.f);
+      xb[slot] = *reinterpret_cast<uint2*>(t);
+    }
+  };
+  pdl_trigger();                 // the next kernel on the stream may start its own weight prefetch
+  issue_w(0, 0);                 // weights never depend on the predecessor: in flight before the wait
+  if (NB > 1) issue_w(1, 1);
+  pdl_wait();                    // activations / workspace / outputs: only after the predecessor is done
+  issue_x(0, 0);
+  if (NB > 1) issue_x(1, 1);
+
+  float acc[4][4][4];  // [word][t][d-reg]: d0/d1 = column 8w+2t, tokens 2tig / 2tig+1 ; d2/d3 = column 8w+2t+1
+  float xs_acc[4] = {0.f, 0.f, 0.f, 0.f};      // ones-row MMA: d0/d1 = sum_k x[token 2tig / 2tig+1][k]
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[w][t][r] = 0.f;
+
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int sl = b & 1;
+    constexpr uint32_t MA = 0x000f000fu, MB = 0x00f000f0u, MG = 0x64006400u, ONES = 0x3C003C00u;
+    mma_16816(xs_acc, ONES, ONES, ONES, ONES, xb[sl].x, xb[sl].y);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t wa = (&q[sl][0].x)[w], wb = (&q[sl][1].x)[w], wc_ = (&q[sl][2].x)[w], wd = (&q[sl][3].x)[w];
+      const uint32_t lo01 = __byte_perm(wa, wb, 0x5410), hi01 = __byte_perm(wa, wb, 0x7632);
+      const uint32_t lo23 = __byte_perm(wc_, wd, 0x5410), hi23 = __byte_perm(wc_, wd, 0x7632);
+      const uint32_t lo01s = lo01 >> 8, hi01s = hi01 >> 8, lo23s = lo23 >> 8, hi23s = hi23 >> 8;
+      // t = 0: columns 0,1 (kind A) ; t = 1: columns 2,3 (kind B) ; t = 2: columns 4,5 (A) ; t = 3: 6,7 (B)
+      mma_16816(acc[w][0], lop3_and_or(lo01, MA, MG), lop3_and_or(hi01, MA, MG), lop3_and_or(lo23, MA, MG),
+                lop3_and_or(hi23, MA, MG), xb[sl].x, xb[sl].y);
+      mma_16816(acc[w][1], lop3_and_or(lo01, MB, MG), lop3_and_or(hi01, MB, MG), lop3_and_or(lo23, MB, MG),
+                lop3_and_or(hi23, MB, MG), xb[sl].x, xb[sl].y);
+      mma_16816(acc[w][2], lop3_and_or(lo01s, MA, MG), lop3_and_or(hi01s, MA, MG), lop3_and_or(lo23s, MA, MG),
+                lop3_and_or(hi23s, MA, MG), xb[sl].x, xb[sl].y);
+      mma_16816(acc[w][3], lop3_and_or(lo01s, MB, MG), lop3_and_or(hi01s, MB, MG), lop3_and_or(lo23s, MB, MG),
+                lop3_and_or(hi23s, MB, MG), xb[sl].x, xb[sl].y);
+    }
+    if (b + 2 < NB) {
+      issue_w(sl, b + 2);
+      issue_x(sl, b + 2);
+    }
+  }
+
+  // ---- raw per-warp sums -> shared memory -----------------------------------------------------------
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int pc = gv_pos(32 * g + 8 * w + 2 * t);
+      if (2 * tig < MT) *reinterpret_cast<float2*>(&red[warp][2 * tig][pc]) = make_float2(acc[w][t][0], acc[w][t][2]);
+      if (2 * tig + 1 < MT)
+        *reinterpret_cast<float2*>(&red[warp][2 * tig + 1][pc]) = make_float2(acc[w][t][1], acc[w][t][3]);
+    }
+  if (g == 0) {
+    if (2 * tig < MT) xsum_s[warp][2 * tig] = xs_acc[0];
+    if (2 * tig + 1 < MT) xsum_s[warp][2 * tig + 1] = xs_acc[1];
   }
   __syncthreads();
 
-  // ---- fold zero-point / scale per (warp-slice, group, column); one thread per output ---------------
+  // ---- fold zero-point / scale per (group, column): thread c owns column n_base + c ------------------
   const bool split = gridDim.y > 1;
-  for (int o = tid; o < MT * kGvTN; o += NWARP * 32) {
-    const int m = o / kGvTN, c = o % kGvTN;
-    const int n = n_base + c;
-    if (m >= M || n >= N) continue;
+  const int c = tid;
+  const int n = n_base + c;
+  if (n < N) {
     const int j = c & 7;
     const bool kindB = ((j >> 1) & 1) != 0;
     const int zshift = 4 * ((j >> 1) + 4 * (j & 1));  // 4 * AWQ_REVERSE_ORDER[j]
-    float val = 0.f;
-    int last_g = -1;
-    float s = 0.f, zoff = 0.f;
-    for (int w = 0; w < NWARP; ++w) {
-      for (int gl = 0; gl < gpw; ++gl) {
-        const int krow = k0 + w * RW + gl * G;
-        if (krow >= K) break;
-        const int gabs = krow / G;
-        if (gabs != last_g) {
-          last_g = gabs;
-          s = __half2float(scales[(int64_t)gabs * N + n]);
-          const float z =
-              static_cast<float>((static_cast<uint32_t>(qzeros[(int64_t)gabs * NW + (n >> 3)]) >> zshift) & 0xFu);
-          zoff = kindB ? 1024.f + 16.f * z : 1024.f + z;
-          if (kindB) s *= 0.0625f;
+    const int pc = gv_pos(c);
+    float val[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) val[m] = 0.f;
+    // warps sharing a quantisation group are summed raw, then folded once
+    int w = 0;
+#pragma unroll 1
+    while (w < kGvWarps) {
+      const int krow = k0 + w * RW;
+      if (krow >= K) break;
+      const int gabs = krow / G;
+      float s = __half2float(__ldg(scales + (int64_t)gabs * N + n));
+      const float z = static_cast<float>((static_cast<uint32_t>(__ldg(qzeros + (int64_t)gabs * NW + (n >> 3))) >> zshift) & 0xFu);
+      const float zoff = kindB ? 1024.f + 16.f * z : 1024.f + z;
+      if (kindB) s *= 0.0625f;
+      float S[MT], X[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) S[m] = X[m] = 0.f;
+      const int gend = (gabs + 1) * G;
+      for (; w < kGvWarps && k0 + w * RW < gend && k0 + w * RW < K; ++w) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          S[m] += red[w][m][pc];
+          X[m] += xsum_s[w][m];
         }
-        const float S = red[(size_t)((w * gpw + gl) * MT + m) * kGvTN + c];
-        val += s * (S - zoff * xsum[(w * gpw + gl) * MT + m]);
       }
+#pragma unroll
+      for (int m = 0; m < MT; ++m) val[m] += s * (S[m] - zoff * X[m]);
     }
-    if (!split) {
-      if (bias != nullptr) val += __half2float(bias[n]);
-      y[(int64_t)m * N + n] = __float2half_rn(val);
-    } else {
-      atomicAdd(&acc_ws[(int64_t)m * N + n], val);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) {
+        if (!split) {
+          float v = val[m];
+          if (bias != nullptr) v += __half2float(bias[n]);
+          y[(int64_t)m * N + n] = __float2half_rn(v);
+        } else {
+          atomicAdd(&acc_ws[(int64_t)m * N + n], val[m]);
+        }
+      }
     }
   }
   if (!split) return;
@@ -214,70 +227,70 @@ __global__ void __launch_bounds__(NWARP * 32)
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int o = tid; o < MT * kGvTN; o += NWARP * 32) {
-    const int m = o / kGvTN, c = o % kGvTN;
-    const int n = n_base + c;
-    if (m >= M || n >= N) continue;
-    float* p = &acc_ws[(int64_t)m * N + n];
-    float val = ldcg_f1(p);
-    *p = 0.f;
-    if (bias != nullptr) val += __half2float(bias[n]);
-    y[(int64_t)m * N + n] = __float2half_rn(val);
+  if (n < N) {
+    const float bv = (bias != nullptr) ? __half2float(bias[n]) : 0.f;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) {
+        float* p = &acc_ws[(int64_t)m * N + n];
+        const float v = ldcg_f1(p);
+        *p = 0.f;
+        y[(int64_t)m * N + n] = __float2half_rn(v + bv);
+      }
+    }
   }
   if (tid == 0) tickets[blockIdx.x] = 0;
 }
 
-template <int NWARP, int MT>
-static cudaError_t launch_gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, int KC, cudaStream_t st) {
-  const int RW = KC / NWARP;
-  const int gpw = RW >= a.G ? RW / a.G : 1;
-  const int xs_bytes = (8 * (KC + kGvXPad) * 2 + 15) & ~15;
-  const size_t smem = (size_t)xs_bytes + (size_t)((NWARP * gpw * MT + 3) & ~3) * 4 + (size_t)NWARP * gpw * MT * kGvTN * 4;
-  auto kern = gemv_gemm_layout_kernel<NWARP, MT>;
+template <int MT, int RW>
+static cudaError_t launch_gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st) {
+  constexpr int KC = kGvWarps * RW;
+  constexpr size_t smem = (size_t)(kGvWarps * MT * kGvRedStride + kGvWarps * MT) * sizeof(float);
+  auto kern = gemv_gemm_layout_kernel<MT, RW>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
   dim3 grid((a.N + kGvTN - 1) / kGvTN, (a.K + KC - 1) / KC);
-  kern<<<grid, NWARP * 32, smem, st>>>(reinterpret_cast<const __half*>(a.x), a.ldx, a.qweight,
-                                       reinterpret_cast<const __half*>(a.scales), a.qzeros,
-                                       reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y),
-                                       acc_ws, tickets, a.M, a.K, a.N, a.G, KC);
-  return cudaGetLastError();
+  return launch_kernel(kern, grid, dim3(kGvWarps * 32), smem, st, reinterpret_cast<const __half*>(a.x), a.ldx,
+                       a.qweight, reinterpret_cast<const __half*>(a.scales), a.qzeros,
+                       reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M,
+                       a.K, a.N, a.G);
 }
 
-// Rows per CTA (KC): NWARP * RW with RW (rows per warp) a multiple of 16 that is a multiple or a divisor of
-// G; sized so the grid has a few CTAs per SM (148 SMs) without starving each CTA of work.
-static int pick_kc(int K, int N, int G, int nwarp, int mt) {
-  int rw;  // rows per warp
+// Rows per warp: the largest of {128, 64, 32} that divides G and still leaves >= 2 CTAs per SM.
+static int pick_rw(int K, int N, int G) {
   const int forced = knob(0);
-  if (forced > 0) {
-    rw = forced / nwarp;
-  } else {
-    const int colblk = (N + kGvTN - 1) / kGvTN;
-    rw = 32;
-    while (rw < 512 && (int64_t)colblk * ((K + rw * nwarp - 1) / (rw * nwarp)) > 148 * 6) rw *= 2;
+  if (forced == 32 || forced == 64 || forced == 128) return (G % forced == 0) ? forced : 32;
+  const int colblk = (N + kGvTN - 1) / kGvTN;
+  for (int rw = 128; rw > 32; rw >>= 1) {
+    if (G % rw != 0) continue;
+    const int kc = kGvWarps * rw;
+    if ((int64_t)colblk * ((K + kc - 1) / kc) >= 2 * 148) return rw;
   }
-  if (rw < 16) rw = 16;
-  if (rw >= G) rw = rw / G * G; else while (G % rw != 0) rw /= 2;
-  // bound the per-warp reduction buffer: gpw * MT <= 8
-  while (rw > G && (rw / G) * mt > 8) rw -= G;
-  return rw * nwarp;
+  return 32;
 }
 
-// N % 32 == 0 and G % 16 == 0 (every AWQ checkpoint: G in {32, 64, 128, K}) take the tensor-pipe GEMV;
-// other shapes are routed to the tcgen05 kernel by the C-ABI layer (token tile padded by TMA zero fill).
+// N % 32 == 0, G % 32 == 0 (every AWQ checkpoint: G in {32, 64, 128, K}) and 8-byte aligned activation rows
+// take the tensor-pipe GEMV; other shapes are routed to the tcgen05 kernel by the C-ABI layer.
 bool gemv_gemm_layout_supported(const GemmArgs& a) {
-  return (a.N % 32) == 0 && (a.G % 16) == 0 && (reinterpret_cast<uintptr_t>(a.qweight) % 16) == 0 && a.M <= 8;
+  return (a.N % 32) == 0 && (a.G % 32) == 0 && (reinterpret_cast<uintptr_t>(a.qweight) % 16) == 0 && a.M <= 8 &&
+         (a.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(a.x) % 8) == 0;
+}
+
+template <int MT>
+static cudaError_t dispatch_rw(const GemmArgs& a, float* acc_ws, int* tickets, int rw, cudaStream_t st) {
+  if (rw == 128) return launch_gemv_gemm_layout<MT, 128>(a, acc_ws, tickets, st);
+  if (rw == 64) return launch_gemv_gemm_layout<MT, 64>(a, acc_ws, tickets, st);
+  return launch_gemv_gemm_layout<MT, 32>(a, acc_ws, tickets, st);
 }
 
 cudaError_t gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st) {
-  const int mt = a.M <= 1 ? 1 : (a.M <= 2 ? 2 : (a.M <= 4 ? 4 : 8));
-  const int KC = pick_kc(a.K, a.N, a.G, 4, mt);
-  if (mt == 1) return launch_gemv_gemm_layout<4, 1>(a, acc_ws, tickets, KC, st);
-  if (mt == 2) return launch_gemv_gemm_layout<4, 2>(a, acc_ws, tickets, KC, st);
-  if (mt == 4) return launch_gemv_gemm_layout<4, 4>(a, acc_ws, tickets, KC, st);
-  return launch_gemv_gemm_layout<4, 8>(a, acc_ws, tickets, KC, st);
+  const int rw = pick_rw(a.K, a.N, a.G);
+  if (a.M <= 1) return dispatch_rw<1>(a, acc_ws, tickets, rw, st);
+  if (a.M <= 2) return dispatch_rw<2>(a, acc_ws, tickets, rw, st);
+  if (a.M <= 4) return dispatch_rw<4>(a, acc_ws, tickets, rw, st);
+  return dispatch_rw<8>(a, acc_ws, tickets, rw, st);
 }
 
 }  // namespace b200awq
@@ -298,6 +311,8 @@ __global__ void __launch_bounds__(256)
                             const __half* __restrict__ bias, __half* __restrict__ y, int M, int K, int N, int G,
                             int zw) {
   extern __shared__ __align__(16) uint4 xs_perm[];  // [MT][nit*128] uint4
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nit = (K + 1023) / 1024;                 // 1024-k passes per row
   const int slots = nit * 128;                       // uint4 slots per token
@@ -410,10 +425,10 @@ static cudaError_t launch_gemv_gemv_layout(const GemmArgs& a, int zw, cudaStream
     if (e != cudaSuccess) return e;
   }
   const int rows_per_cta = 8 * RW;
-  kern<<<(a.N + rows_per_cta - 1) / rows_per_cta, 256, smem, st>>>(
-      reinterpret_cast<const __half*>(a.x), a.ldx, a.qweight, reinterpret_cast<const __half*>(a.scales), a.qzeros,
-      reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y), a.M, a.K, a.N, a.G, zw);
-  return cudaGetLastError();
+  return launch_kernel(kern, dim3((a.N + rows_per_cta - 1) / rows_per_cta), dim3(256), smem, st,
+                       reinterpret_cast<const __half*>(a.x), a.ldx, a.qweight, reinterpret_cast<const __half*>(a.scales),
+                       a.qzeros, reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y), a.M, a.K, a.N,
+                       a.G, zw);
 }
 
 static int zeros_width(int K, int G) {  // awq/modules/linear/gemv.py:12-24
@@ -467,6 +482,8 @@ __global__ void __launch_bounds__(128)
                             const __half* __restrict__ scales, const __half* __restrict__ szeros,
                             const __half* __restrict__ bias, __half* __restrict__ y, int M, int K, int N, int G) {
   extern __shared__ __align__(16) uint4 xs4[];  // [MT][K/8] uint4, natural order
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int KV = K >> 3;
   for (int i = tid; i < MT * KV; i += blockDim.x) {
@@ -571,12 +588,9 @@ static cudaError_t launch_gemv_fast(const FastArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
   }
   const int groups = a.N / 4;
-  kern<<<(groups + 3) / 4, 128, smem, st>>>(reinterpret_cast<const __half*>(a.x), a.ldx, a.qweight,
-                                            reinterpret_cast<const __half*>(a.scales),
-                                            reinterpret_cast<const __half*>(a.szeros),
-                                            reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y),
-                                            a.M, a.K, a.N, a.G);
-  return cudaGetLastError();
+  return launch_kernel(kern, dim3((groups + 3) / 4), dim3(128), smem, st, reinterpret_cast<const __half*>(a.x), a.ldx,
+                       a.qweight, reinterpret_cast<const __half*>(a.scales), reinterpret_cast<const __half*>(a.szeros),
+                       reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y), a.M, a.K, a.N, a.G);
 }
 
 cudaError_t gemv_fast_layout(const FastArgs& a0, cudaStream_t st) {

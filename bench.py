@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--mode", choices=["decode", "prefill"], default="decode")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--pdl", type=int, default=1, help="1: launch kernels with programmatic dependent launch")
     ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: fewer layers => INVALID as a bench value")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -281,6 +282,8 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     rep = Replica(dev, M, layers=a.layers, seed=rank)
+    rep.ext.set_knob(4, 1 if a.pdl else 0)
+    config["pdl"] = bool(a.pdl)
     peaks = measured_peaks()
 
     # value leg: inputs resident in HBM, the step replayed as one CUDA graph

@@ -85,10 +85,12 @@ int b200awq_rmsnorm(const void* x, const void* weight, void* out, int rows, int 
 int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200awq_stream_t stream);
 
 /* Tuning / debug knobs (process-global; used by the micro-benchmarks and layout self-tests).
- *   key 0: GEMV K-rows per CTA override (0 = heuristic)
+ *   key 0: GEMV rows per warp override: 32 / 64 / 128 (0 = heuristic)
  *   key 1: tensor-core path split-K override (0 = heuristic)
  *   key 2: M threshold at or below which the CUDA-core GEMV is used (default 8)
- *   key 3: UMMA A-descriptor variant (self-test only)
+ *   key 3: reserved
+ *   key 4: 1 = launch every kernel with the programmatic-dependent-launch attribute (the kernels issue
+ *          their weight loads before griddepcontrol.wait, so consecutive linears overlap); default 0
  */
 int b200awq_set_knob(int key, int value);
 int b200awq_get_knob(int key);

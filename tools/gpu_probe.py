@@ -101,7 +101,7 @@ def bench_shapes():
         qw = [torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
         qz = [torch.randint(-2**31, 2**31 - 1, (K // G, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
         sc = [(torch.rand((K // G, N), device=dev) * 0.01 + 0.001).half() for _ in range(nbuf)]
-        for M in (1, 2, 4, 8, 16, 32, 64, 128, 256, 1024, 4096):
+        for M in (1, 2, 8, 16, 64, 256, 4096):
             if M > 8 and N == 28672 and M > 256:
                 continue
             x = torch.randn((M, K), device=dev, dtype=torch.float16)
@@ -132,10 +132,40 @@ def bench_shapes():
     return res
 
 
+def bench_gemv_knobs():
+    """M = 1 decode GEMV: rows-per-warp (knob 0) x PDL (knob 4) sweep on the four Llama-3-8B shapes."""
+    res = {}
+    G = 128
+    for (K, N) in [(4096, 4096), (4096, 6144), (4096, 28672), (14336, 4096)]:
+        wbytes = K * N // 2 + (K // G) * N * 2 + (K // G) * N // 2
+        nbuf = max(3, int(400e6 // wbytes) + 1)
+        qw = [torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
+        qz = [torch.randint(-2**31, 2**31 - 1, (K // G, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
+        sc = [(torch.rand((K // G, N), device=dev) * 0.01 + 0.001).half() for _ in range(nbuf)]
+        x = torch.randn((1, K), device=dev, dtype=torch.float16)
+        for rw in (32, 64, 128):
+            for pdl in (0, 1):
+                ext.set_knob(0, rw)
+                ext.set_knob(4, pdl)
+                try:
+                    us = time_kernel(lambda i: ext.linear_forward("gemm", x, qw[i], sc[i], qz[i], G), nbuf, iters=200, warm=10)
+                    res[f"K{K}_N{N}_rw{rw}_pdl{pdl}"] = {"us": round(us, 2), "GBps": round((wbytes + 2 * K + 2 * N) / us / 1e3, 1)}
+                except Exception as e:  # noqa: BLE001
+                    res[f"K{K}_N{N}_rw{rw}_pdl{pdl}"] = f"ERR {e}"
+        ext.set_knob(0, 0)
+        ext.set_knob(4, 0)
+        del qw, qz, sc
+        torch.cuda.empty_cache()
+    return res
+
+
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     out["checks"] = check_paths()
     print(json.dumps(out["checks"], indent=1), flush=True)
+    if "--knobs" in sys.argv:
+        out["gemv_knobs"] = bench_gemv_knobs()
+        print(json.dumps(out["gemv_knobs"], indent=1), flush=True)
     if "--no-bench" not in sys.argv:
         out["bench"] = bench_shapes()
         print(json.dumps(out["bench"], indent=1), flush=True)
