@@ -100,6 +100,7 @@ int b200awq_gemm_forward(const void* x, int64_t ldx, const int32_t* qweight, con
   if (M <= knob(2) && M <= 8 && gemv_gemm_layout_supported(a)) {
     if (!have_ws) return B200AWQ_EWORKSPACE;  // the GEMV splits K across CTAs
     if ((N + 255) / 256 > 4096) return B200AWQ_EUNSUPPORTED;
+    if (knob(5) == 0 && gemv_v3_supported(a)) return fold(gemv_v3(a, ws.acc, ws.tickets, st));
     return fold(gemv_gemm_layout(a, ws.acc, ws.tickets, st));
   }
   return fold(gemm_tc(a, 0, ws.acc, ws.tickets, st));

@@ -399,25 +399,35 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
   } else {
     // ================================================================= dequant producers (8 warps)
+    // Global loads run kPrefetch k-steps ahead of the dequantisation (register ring): a k-step is only
+    // ~500 MMA cycles, well below the DRAM / L2 latency a 1-deep prefetch would expose every step.
+    constexpr int kPrefetch = 4;
     const int dt = threadIdx.x - 192;  // 0..255
-    typename LoaderOf<LAYOUT>::T cur, nxt;
-    nxt.init();
+    typename LoaderOf<LAYOUT>::T ring[kPrefetch];
     int stage = 0;
     uint32_t phase = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
       const int ks = w % p.ksplit;
       const int nt = w / (p.ksplit * p.m_tiles);
       const int s_begin = (int)((int64_t)KS * ks / p.ksplit), s_end = (int)((int64_t)KS * (ks + 1) / p.ksplit);
-      nxt.init();  // new tile: different columns, cached group data is stale
-      if (s_begin < s_end) nxt.load(p, nt, s_begin * kBK, dt);
-      for (int s = s_begin; s < s_end; ++s) {
-        cur = nxt;
-        if (s + 1 < s_end) nxt.load(p, nt, (s + 1) * kBK, dt);  // next step's loads in flight
-        mbar_wait(&empty[stage], phase ^ 1);
-        cur.store(p, nt, s * kBK, dt, a_base + (size_t)stage * kAStageBytes);
-        fence_proxy_async_smem();
-        mbar_arrive(&full[stage]);
-        if (++stage == NS) { stage = 0; phase ^= 1; }
+#pragma unroll
+      for (int d = 0; d < kPrefetch; ++d) {
+        ring[d].init();  // new tile: different columns, cached group data is stale
+        if (s_begin + d < s_end) ring[d].load(p, nt, (s_begin + d) * kBK, dt);
+      }
+      for (int s0 = s_begin; s0 < s_end; s0 += kPrefetch) {
+#pragma unroll
+        for (int d = 0; d < kPrefetch; ++d) {
+          const int s = s0 + d;
+          if (s < s_end) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            ring[d].store(p, nt, s * kBK, dt, a_base + (size_t)stage * kAStageBytes);
+            fence_proxy_async_smem();
+            mbar_arrive(&full[stage]);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+            if (s + kPrefetch < s_end) ring[d].load(p, nt, (s + kPrefetch) * kBK, dt);
+          }
+        }
       }
     }
   }
@@ -449,23 +459,28 @@ static EncodeTiledFn get_encode_fn() {
 
 struct TmapKey {
   const void* ptr;
-  int64_t ld;
-  int M, K, BT;
-  bool operator==(const TmapKey& o) const { return ptr == o.ptr && ld == o.ld && M == o.M && K == o.K && BT == o.BT; }
+  uint64_t inner, outer, pitch;
+  uint32_t bi, bo;
+  int kind;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && pitch == o.pitch && bi == o.bi && bo == o.bo &&
+           kind == o.kind;
+  }
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
-    h ^= (size_t)k.ld * 0x9E3779B97F4A7C15ull + (size_t)k.M * 1315423911u + (size_t)k.K * 2654435761u + (size_t)k.BT;
+    h ^= (size_t)k.inner * 0x9E3779B97F4A7C15ull + (size_t)k.outer * 1315423911u + (size_t)k.pitch * 2654435761u +
+         (size_t)k.bi * 31u + (size_t)k.bo * 131u + (size_t)k.kind;
     return h;
   }
 };
 
-// X[M, K] fp16 (row pitch ld elements) -> box {64 k, BT rows}, 128B swizzle, zero fill out of bounds
-static cudaError_t make_x_tmap(const void* x, int64_t ld, int M, int K, int BT, CUtensorMap* out) {
+cudaError_t make_tmap_2d(const void* ptr, int elem_kind, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                         uint32_t box_inner, uint32_t box_outer, CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{x, ld, M, K, BT};
+  TmapKey key{ptr, inner, outer, pitch_bytes, box_inner, box_outer, elem_kind};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -476,18 +491,23 @@ static cudaError_t make_x_tmap(const void* x, int64_t ld, int M, int K, int BT, 
   }
   EncodeTiledFn enc = get_encode_fn();
   if (enc == nullptr) return cudaErrorNotSupported;
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BT};
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = elem_kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_INT32;
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
   std::lock_guard<std::mutex> lk(mu);
-  if (cache.size() > 4096) cache.clear();
+  if (cache.size() > 8192) cache.clear();
   cache.emplace(key, *out);
   return cudaSuccess;
+}
+
+// X[M, K] fp16 (row pitch ld elements) -> box {64 k, BT rows}
+static cudaError_t make_x_tmap(const void* x, int64_t ld, int M, int K, int BT, CUtensorMap* out) {
+  return make_tmap_2d(x, 0, (uint64_t)K, (uint64_t)M, (uint64_t)ld * 2, kBK, (uint32_t)BT, out);
 }
 
 static int sm_count() {

@@ -9,6 +9,11 @@
 // weight plus 5/8 op of LOP3/SHF unpack.  Zero-point and scale are applied once per (group, column):
 //     y[n] += s[g,n] * ( 2^24 * sum_k x[k] q[k,n]  -  z[g,n] * sum_k x[k] )
 // The cross-thread / cross-CTA (split-K) reduction is fp32; the result is rounded to fp16 once.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -46,6 +51,10 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void named_bar_sync_gv(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 constexpr int kGvTN = 256;       // columns per CTA (one warp width)
@@ -291,6 +300,319 @@ cudaError_t gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cud
   if (a.M <= 2) return dispatch_rw<2>(a, acc_ws, tickets, rw, st);
   if (a.M <= 4) return dispatch_rw<4>(a, acc_ws, tickets, rw, st);
   return dispatch_rw<8>(a, acc_ws, tickets, rw, st);
+}
+
+}  // namespace b200awq
+
+// ======================================================================= GEMM layout, persistent TMA-ring GEMV
+// v3.  What the v2 kernel above taught (ncu, B200): with loads staged in REGISTERS a CTA can keep ~50 KB
+// per SM in flight and every short-lived CTA pays its own chain of dependent latencies (DRAM -> MMA ->
+// fold constants -> atomics -> fence -> ticket): DRAM sat at 9-29 % busy.  HBM3e needs ~90 KB per SM in
+// flight.  So: ONE persistent CTA per SM; a producer warp streams 8 KB weight tiles (64 rows x 256 columns,
+// TMA 2-D, 128B swizzle) plus the tile's scales / zeros (bulk copies) into a 16-stage shared-memory ring
+// (~147 KB in flight per SM, independent of registers, running ahead across tile boundaries and - under
+// PDL - across KERNEL boundaries, since weights never depend on the predecessor); two consumer groups of
+// four warps take alternate tiles, read fragments with conflict-free LDS.128, run the same PRMT/LOP3 ->
+// mma.sync core as v2 and fold per tile from shared memory.  Column sums live in shared memory while a
+// CTA stays inside one 256-column block; they are pushed to the fp32 workspace with atomics when the
+// block changes, and tickets count TILES (not CTAs), so the last contributor of a column block is known
+// without any host-side schedule.
+namespace b200awq {
+
+constexpr int kV3TileRows = 64;
+constexpr int kV3TileCols = 256;
+constexpr int kV3TileBytes = kV3TileRows * 128;               // 8 KB of packed weights
+constexpr int kV3ScaleBytes = kV3TileCols * 2;                // 512 B
+constexpr int kV3ZeroBytes = kV3TileCols / 8 * 4;             // 128 B
+constexpr int kV3StageBytes = 9216;                           // 8192 + 640, padded to 1024 (swizzle atoms)
+constexpr int kV3Threads = 32 + 256;                          // producer warp + 2 x 4 consumer warps
+
+template <int MT>
+struct V3Smem {
+  static constexpr int kStages = MT <= 2 ? 16 : (MT == 4 ? 12 : 8);  // even: stage parity == group parity
+  static constexpr int red_floats = 2 * 4 * MT * kGvRedStride;       // [grp][warp4][MT][272]
+  static constexpr int colacc_floats = 2 * MT * kV3TileCols;         // [grp][MT][256]
+  static constexpr int xsum_floats = 2 * 4 * MT;                     // [grp][warp4][MT]
+  static constexpr size_t bytes = (size_t)kStages * kV3StageBytes + 1024 /*align*/ +
+                                  (size_t)(red_floats + colacc_floats + xsum_floats) * 4 + 2 * kStages * 8 + 64;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(kV3Threads, 1)
+    gemv_v3_kernel(const __grid_constant__ CUtensorMap tmw, const __half* __restrict__ x, int64_t ldx,
+                   const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
+                   const __half* __restrict__ bias, __half* __restrict__ y, float* __restrict__ acc_ws,
+                   int* __restrict__ tickets, int M, int K, int N, int G) {
+  constexpr int kV3Stages = V3Smem<MT>::kStages;
+  extern __shared__ uint8_t v3_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(v3_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  float* red = reinterpret_cast<float*>(smem + (size_t)kV3Stages * kV3StageBytes);
+  float* colacc = red + V3Smem<MT>::red_floats;
+  float* xsum_s = colacc + V3Smem<MT>::colacc_floats;
+  uint64_t* full = reinterpret_cast<uint64_t*>(xsum_s + V3Smem<MT>::xsum_floats);
+  uint64_t* empty = full + kV3Stages;
+  int* flags = reinterpret_cast<int*>(empty + kV3Stages);  // [2] last-contributor flags, one per group
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NW = N >> 3;
+  const int TPC = K / kV3TileRows;                 // tiles per column block
+  const int T = (N / kV3TileCols) * TPC;           // all tiles, column-block major
+  const int t0 = (int)((int64_t)T * blockIdx.x / gridDim.x);
+  const int t1 = (int)((int64_t)T * (blockIdx.x + 1) / gridDim.x);
+  const int ntile = t1 - t0;
+
+  pdl_trigger();
+  if (tid == 0) {
+    tma_prefetch_desc(&tmw);
+    for (int s = 0; s < kV3Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);  // one elected arrival by the group that consumed the stage
+    }
+    fence_mbar_init();
+  }
+  for (int i = tid; i < V3Smem<MT>::colacc_floats; i += kV3Threads) colacc[i] = 0.f;
+  __syncthreads();
+
+  if (warp == 0) {
+    // ============================================================ producer: weights never wait for PDL
+    if (lane == 0) {
+      for (int i = 0; i < ntile; ++i) {
+        const int stage = i % kV3Stages;
+        const uint32_t ph = (uint32_t)(i / kV3Stages) & 1u;
+        mbar_wait(&empty[stage], ph ^ 1);
+        const int t = t0 + i;
+        const int cb = t / TPC, kt = t - cb * TPC;
+        const int grp_abs = (kt * kV3TileRows) / G;
+        uint8_t* st = ring + (size_t)stage * kV3StageBytes;
+        mbar_arrive_expect_tx(&full[stage], kV3TileBytes + kV3ScaleBytes + kV3ZeroBytes);
+        tma_load_2d(st, &tmw, &full[stage], cb * (kV3TileCols / 8), kt * kV3TileRows);
+        bulk_load_1d(st + kV3TileBytes, scales + (int64_t)grp_abs * N + cb * kV3TileCols, kV3ScaleBytes, &full[stage]);
+        bulk_load_1d(st + kV3TileBytes + kV3ScaleBytes, qzeros + (int64_t)grp_abs * NW + cb * (kV3TileCols / 8),
+                     kV3ZeroBytes, &full[stage]);
+      }
+    }
+    return;
+  }
+
+  // ================================================================ consumers
+  const int cw = warp - 1;             // 0..7
+  const int grp = cw >> 2;             // consumer group: takes tiles i = grp, grp + 2, ...
+  const int w4 = cw & 3;               // k16-block of the tile owned by this warp
+  const int gt = tid - 32 - grp * 128; // thread index inside the group, 0..127
+  const int g = lane >> 2, tig = lane & 3;
+  const bool tok_ok = g < M;
+  float* my_red = red + (size_t)(grp * 4 + w4) * MT * kGvRedStride;
+  float* grp_red = red + (size_t)(grp * 4) * MT * kGvRedStride;
+  float* my_col = colacc + (size_t)grp * MT * kV3TileCols;
+  float* grp_xsum = xsum_s + grp * 4 * MT;
+
+  pdl_wait();  // activations, workspace, tickets, outputs belong to the stream order
+
+  int cur_cb = -1, tiles_in_cb = 0;
+  auto push = [&](int cb, int ntl) {
+    // column sums of this group -> fp32 workspace; tickets count tiles; last contributor finalises
+    const int n_base = cb * kV3TileCols;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = gt + 128 * h;
+          atomicAdd(&acc_ws[(int64_t)m * N + n_base + c], my_col[m * kV3TileCols + c]);
+          my_col[m * kV3TileCols + c] = 0.f;
+        }
+      }
+    }
+    __threadfence();
+    named_bar_sync_gv(1 + grp, 128);
+    if (gt == 0) {
+      const int prev = atomicAdd(&tickets[cb], ntl);
+      flags[grp] = (prev + ntl == TPC);
+    }
+    named_bar_sync_gv(1 + grp, 128);
+    if (flags[grp]) {
+      __threadfence();
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m < M) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int n = n_base + gt + 128 * h;
+            float* p = &acc_ws[(int64_t)m * N + n];
+            float v = ldcg_f1(p);
+            *p = 0.f;
+            if (bias != nullptr) v += __half2float(bias[n]);
+            y[(int64_t)m * N + n] = __float2half_rn(v);
+          }
+        }
+      }
+      if (gt == 0) tickets[cb] = 0;
+    }
+    named_bar_sync_gv(1 + grp, 128);  // flags[grp] may be rewritten by the next push
+  };
+
+  // activations of this warp's block of tile i: rows 2tig, 2tig+1 and 2tig+8, 2tig+9 of the k16-block
+  auto load_x = [&](int i, uint32_t& b0, uint32_t& b1) {
+    b0 = b1 = 0u;
+    if (i < ntile && tok_ok) {
+      const int t = t0 + i;
+      const int kt = t % TPC;
+      const __half* px = x + (int64_t)g * ldx + kt * kV3TileRows + 16 * w4 + 2 * tig;
+      b0 = *reinterpret_cast<const uint32_t*>(px);
+      b1 = *reinterpret_cast<const uint32_t*>(px + 8);
+    }
+  };
+  uint32_t xb0, xb1, nxb0, nxb1;
+  load_x(grp, xb0, xb1);
+
+  for (int i = grp; i < ntile; i += 2) {
+    const int stage = i % kV3Stages;
+    const uint32_t ph = (uint32_t)(i / kV3Stages) & 1u;
+    const int t = t0 + i;
+    const int cb = t / TPC;
+    if (cb != cur_cb) {
+      if (cur_cb >= 0) push(cur_cb, tiles_in_cb);
+      cur_cb = cb;
+      tiles_in_cb = 0;
+    }
+    ++tiles_in_cb;
+    load_x(i + 2, nxb0, nxb1);  // next tile's activations in flight while this one is computed
+    mbar_wait(&full[stage], ph);
+    const uint8_t* st = ring + (size_t)stage * kV3StageBytes;
+
+    // ---- fragments from the swizzled tile: rows (2tig, 2tig+1, 2tig+8, 2tig+9) of block w4, chunk g
+    const int r0 = 16 * w4 + 2 * tig;
+    const uint4 qa = *reinterpret_cast<const uint4*>(st + (r0 + 0) * 128 + ((g ^ ((r0 + 0) & 7)) << 4));
+    const uint4 qb = *reinterpret_cast<const uint4*>(st + (r0 + 1) * 128 + ((g ^ ((r0 + 1) & 7)) << 4));
+    const uint4 qc = *reinterpret_cast<const uint4*>(st + (r0 + 8) * 128 + ((g ^ ((r0 + 8) & 7)) << 4));
+    const uint4 qd = *reinterpret_cast<const uint4*>(st + (r0 + 9) * 128 + ((g ^ ((r0 + 9) & 7)) << 4));
+    float acc[4][4][4];
+    float xs_acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[w][tt][r] = 0.f;
+    {
+      constexpr uint32_t MA = 0x000f000fu, MB = 0x00f000f0u, MG = 0x64006400u, ONES = 0x3C003C00u;
+      mma_16816(xs_acc, ONES, ONES, ONES, ONES, xb0, xb1);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const uint32_t wa = (&qa.x)[w], wb = (&qb.x)[w], wc_ = (&qc.x)[w], wd = (&qd.x)[w];
+        const uint32_t lo01 = __byte_perm(wa, wb, 0x5410), hi01 = __byte_perm(wa, wb, 0x7632);
+        const uint32_t lo23 = __byte_perm(wc_, wd, 0x5410), hi23 = __byte_perm(wc_, wd, 0x7632);
+        const uint32_t lo01s = lo01 >> 8, hi01s = hi01 >> 8, lo23s = lo23 >> 8, hi23s = hi23 >> 8;
+        mma_16816(acc[w][0], lop3_and_or(lo01, MA, MG), lop3_and_or(hi01, MA, MG), lop3_and_or(lo23, MA, MG),
+                  lop3_and_or(hi23, MA, MG), xb0, xb1);
+        mma_16816(acc[w][1], lop3_and_or(lo01, MB, MG), lop3_and_or(hi01, MB, MG), lop3_and_or(lo23, MB, MG),
+                  lop3_and_or(hi23, MB, MG), xb0, xb1);
+        mma_16816(acc[w][2], lop3_and_or(lo01s, MA, MG), lop3_and_or(hi01s, MA, MG), lop3_and_or(lo23s, MA, MG),
+                  lop3_and_or(hi23s, MA, MG), xb0, xb1);
+        mma_16816(acc[w][3], lop3_and_or(lo01s, MB, MG), lop3_and_or(hi01s, MB, MG), lop3_and_or(lo23s, MB, MG),
+                  lop3_and_or(hi23s, MB, MG), xb0, xb1);
+      }
+    }
+    // ---- raw sums of this warp -> shared memory
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt) {
+        const int pc = gv_pos(32 * g + 8 * w + 2 * tt);
+        if (2 * tig < MT)
+          *reinterpret_cast<float2*>(&my_red[(2 * tig) * kGvRedStride + pc]) = make_float2(acc[w][tt][0], acc[w][tt][2]);
+        if (2 * tig + 1 < MT)
+          *reinterpret_cast<float2*>(&my_red[(2 * tig + 1) * kGvRedStride + pc]) =
+              make_float2(acc[w][tt][1], acc[w][tt][3]);
+      }
+    if (g == 0) {
+      if (2 * tig < MT) grp_xsum[w4 * MT + 2 * tig] = xs_acc[0];
+      if (2 * tig + 1 < MT) grp_xsum[w4 * MT + 2 * tig + 1] = xs_acc[1];
+    }
+    named_bar_sync_gv(1 + grp, 128);
+
+    // ---- fold (one group = one tile = one quantisation group): thread gt owns columns gt and gt + 128
+    {
+      const __half* s_sc = reinterpret_cast<const __half*>(st + kV3TileBytes);
+      const uint32_t* s_z = reinterpret_cast<const uint32_t*>(st + kV3TileBytes + kV3ScaleBytes);
+      float X[MT];
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+        X[m] = grp_xsum[0 * MT + m] + grp_xsum[1 * MT + m] + grp_xsum[2 * MT + m] + grp_xsum[3 * MT + m];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = gt + 128 * h;
+        const int j = c & 7;
+        const bool kindB = ((j >> 1) & 1) != 0;
+        const int zshift = 4 * ((j >> 1) + 4 * (j & 1));
+        float sc = __half2float(s_sc[c]);
+        const float z = static_cast<float>((s_z[c >> 3] >> zshift) & 0xFu);
+        const float zoff = kindB ? 1024.f + 16.f * z : 1024.f + z;
+        if (kindB) sc *= 0.0625f;
+        const int pc = gv_pos(c);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const float S = grp_red[(0 * MT + m) * kGvRedStride + pc] + grp_red[(1 * MT + m) * kGvRedStride + pc] +
+                          grp_red[(2 * MT + m) * kGvRedStride + pc] + grp_red[(3 * MT + m) * kGvRedStride + pc];
+          my_col[m * kV3TileCols + c] += sc * (S - zoff * X[m]);
+        }
+      }
+    }
+    named_bar_sync_gv(1 + grp, 128);       // all reads of the stage and of red[] are done
+    if (gt == 0) mbar_arrive(&empty[stage]);
+    xb0 = nxb0;
+    xb1 = nxb1;
+  }
+  if (cur_cb >= 0) push(cur_cb, tiles_in_cb);
+}
+
+static int v3_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = B200AWQ_SM_COUNT_FALLBACK;
+  }
+  return n;
+}
+
+template <int MT>
+static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st) {
+  CUtensorMap tm;
+  // qweight [K, N/8] int32 -> box {32 words = 128 B, 64 rows}, 128B swizzle
+  cudaError_t e = make_tmap_2d(a.qweight, /*int32*/ 1, (uint64_t)(a.N / 8), (uint64_t)a.K, (uint64_t)(a.N / 8) * 4, 32,
+                               kV3TileRows, &tm);
+  if (e != cudaSuccess) return e;
+  auto kern = gemv_v3_kernel<MT>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3Smem<MT>::bytes);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int T = (a.N / kV3TileCols) * (a.K / kV3TileRows);
+  const int grid = T < v3_sm_count() ? T : v3_sm_count();
+  return launch_kernel(kern, dim3(grid), dim3(kV3Threads), V3Smem<MT>::bytes, st, tm,
+                       reinterpret_cast<const __half*>(a.x), a.ldx, reinterpret_cast<const __half*>(a.scales), a.qzeros,
+                       reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M,
+                       a.K, a.N, a.G);
+}
+
+// Shapes the persistent TMA-ring kernel takes: whole 64 x 256 tiles inside one quantisation group.
+bool gemv_v3_supported(const GemmArgs& a) {
+  return gemv_gemm_layout_supported(a) && (a.N % kV3TileCols) == 0 && (a.K % kV3TileRows) == 0 &&
+         (a.G % kV3TileRows) == 0 && a.N / kV3TileCols <= 4096;
+}
+
+cudaError_t gemv_v3(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st) {
+  if (a.M <= 1) return launch_v3<1>(a, acc_ws, tickets, st);
+  if (a.M <= 2) return launch_v3<2>(a, acc_ws, tickets, st);
+  if (a.M <= 4) return launch_v3<4>(a, acc_ws, tickets, st);
+  return launch_v3<8>(a, acc_ws, tickets, st);
 }
 
 }  // namespace b200awq

@@ -1,5 +1,6 @@
 // Internal launcher interface between the C-ABI layer (cabi.cu) and the kernel translation units.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -57,7 +58,14 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
 cudaError_t dequantize_gemm(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out, int K,
                             int N, int G, cudaStream_t st);
 
+// 2-D tiled tensor map over a row-major matrix (cached by address + shape; weights are static, activations
+// recycle a few buffers).  elem_kind: 0 = fp16, 1 = int32.  128B swizzle, zero fill out of bounds.
+cudaError_t make_tmap_2d(const void* ptr, int elem_kind, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                         uint32_t box_inner, uint32_t box_outer, CUtensorMap* out);
+
 bool gemv_gemm_layout_supported(const GemmArgs& a);
+bool gemv_v3_supported(const GemmArgs& a);
+cudaError_t gemv_v3(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st);
 cudaError_t gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st);
 cudaError_t gemv_gemv_layout(const GemmArgs& a, cudaStream_t st);
 cudaError_t gemv_fast_layout(const FastArgs& a, cudaStream_t st);

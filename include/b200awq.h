@@ -91,6 +91,7 @@ int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200aw
  *   key 3: reserved
  *   key 4: 1 = launch every kernel with the programmatic-dependent-launch attribute (the kernels issue
  *          their weight loads before griddepcontrol.wait, so consecutive linears overlap); default 0
+ *   key 5: 1 = disable the persistent TMA-ring GEMV (use the register-staged GEMV for every M <= 8 shape)
  */
 int b200awq_set_knob(int key, int value);
 int b200awq_get_knob(int key);

@@ -101,7 +101,7 @@ def bench_shapes():
         qw = [torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
         qz = [torch.randint(-2**31, 2**31 - 1, (K // G, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
         sc = [(torch.rand((K // G, N), device=dev) * 0.01 + 0.001).half() for _ in range(nbuf)]
-        for M in (1, 2, 8, 16, 64, 256, 4096):
+        for M in (1, 8, 16, 64, 256, 4096):
             if M > 8 and N == 28672 and M > 256:
                 continue
             x = torch.randn((M, K), device=dev, dtype=torch.float16)
@@ -143,17 +143,21 @@ def bench_gemv_knobs():
         qz = [torch.randint(-2**31, 2**31 - 1, (K // G, N // 8), dtype=torch.int32, device=dev) for _ in range(nbuf)]
         sc = [(torch.rand((K // G, N), device=dev) * 0.01 + 0.001).half() for _ in range(nbuf)]
         x = torch.randn((1, K), device=dev, dtype=torch.float16)
-        for rw in (32, 64, 128):
+        for name, k5, rw in (("v3", 0, 0), ("v2rw64", 1, 64)):
             for pdl in (0, 1):
-                ext.set_knob(0, rw)
-                ext.set_knob(4, pdl)
-                try:
-                    us = time_kernel(lambda i: ext.linear_forward("gemm", x, qw[i], sc[i], qz[i], G), nbuf, iters=200, warm=10)
-                    res[f"K{K}_N{N}_rw{rw}_pdl{pdl}"] = {"us": round(us, 2), "GBps": round((wbytes + 2 * K + 2 * N) / us / 1e3, 1)}
-                except Exception as e:  # noqa: BLE001
-                    res[f"K{K}_N{N}_rw{rw}_pdl{pdl}"] = f"ERR {e}"
+                for M in (1, 8):
+                    xm = torch.randn((M, K), device=dev, dtype=torch.float16)
+                    ext.set_knob(5, k5)
+                    ext.set_knob(0, rw)
+                    ext.set_knob(4, pdl)
+                    try:
+                        us = time_kernel(lambda i: ext.linear_forward("gemm", xm, qw[i], sc[i], qz[i], G), nbuf, iters=200, warm=10)
+                        res[f"K{K}_N{N}_{name}_pdl{pdl}_M{M}"] = {"us": round(us, 2), "GBps": round((wbytes + 2 * M * K + 2 * M * N) / us / 1e3, 1)}
+                    except Exception as e:  # noqa: BLE001
+                        res[f"K{K}_N{N}_{name}_pdl{pdl}_M{M}"] = f"ERR {e}"
         ext.set_knob(0, 0)
         ext.set_knob(4, 0)
+        ext.set_knob(5, 0)
         del qw, qz, sc
         torch.cuda.empty_cache()
     return res
