@@ -59,9 +59,9 @@ __device__ __forceinline__ void named_bar_sync_gv(int id, int nthreads) {
 
 constexpr int kGvTN = 256;       // columns per CTA (one warp width)
 constexpr int kGvWarps = 8;      // warps per CTA, each on its own contiguous RW rows
-constexpr int kGvRedStride = kGvTN + 16;  // +2 floats per 32 columns: conflict-free float2 stores
+constexpr int kGvRedStride = kGvTN + 32;  // +4 floats per 32 columns: conflict-free float2 stores, 16-B aligned octets
 
-__device__ __forceinline__ int gv_pos(int c) { return c + ((c >> 5) << 1); }
+__device__ __forceinline__ int gv_pos(int c) { return c + ((c >> 5) << 2); }
 
 // Lean by construction - a 4096x4096 GEMV is ~59 KB per SM (~1 us of HBM time), so every prologue /
 // epilogue instruction shows: no shared-memory staging of x (B fragments come straight from global, issued
@@ -305,18 +305,23 @@ cudaError_t gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cud
 }  // namespace b200awq
 
 // ======================================================================= GEMM layout, persistent TMA-ring GEMV
-// v3.  What the v2 kernel above taught (ncu, B200): with loads staged in REGISTERS a CTA can keep ~50 KB
-// per SM in flight and every short-lived CTA pays its own chain of dependent latencies (DRAM -> MMA ->
-// fold constants -> atomics -> fence -> ticket): DRAM sat at 9-29 % busy.  HBM3e needs ~90 KB per SM in
-// flight.  So: ONE persistent CTA per SM; a producer warp streams 8 KB weight tiles (64 rows x 256 columns,
-// TMA 2-D, 128B swizzle) plus the tile's scales / zeros (bulk copies) into a 16-stage shared-memory ring
-// (~147 KB in flight per SM, independent of registers, running ahead across tile boundaries and - under
-// PDL - across KERNEL boundaries, since weights never depend on the predecessor); two consumer groups of
-// four warps take alternate tiles, read fragments with conflict-free LDS.128, run the same PRMT/LOP3 ->
-// mma.sync core as v2 and fold per tile from shared memory.  Column sums live in shared memory while a
-// CTA stays inside one 256-column block; they are pushed to the fp32 workspace with atomics when the
-// block changes, and tickets count TILES (not CTAs), so the last contributor of a column block is known
-// without any host-side schedule.
+// v3/v4.  What the register-staged kernel above taught (ncu, B200): with loads staged in REGISTERS a CTA
+// keeps ~50 KB per SM in flight and every short-lived CTA pays its own chain of dependent latencies
+// (DRAM -> MMA -> fold constants -> atomics -> fence -> ticket): DRAM sat at 9-29 % busy.  A first
+// ring-buffer version with four warps sharing each 16-row block spent 2/3 of its instructions on
+// per-block flush / fold / barriers.  This version:
+//   * ONE persistent CTA per SM; a producer warp streams 8 KB weight tiles (64 rows x 256 columns, TMA 2-D,
+//     128B swizzle) plus the tile's group scales / zeros (bulk copies) into shared memory; every consumer
+//     warp owns TWO ring stages (8 warps x 2 x 9 KB = 147 KB in flight per SM, independent of registers,
+//     running ahead across tile and - under PDL - KERNEL boundaries: weights never depend on the
+//     predecessor);
+//   * consumer warps are INDEPENDENT: warp w walks its own contiguous run of tiles, keeps the 64 + 4
+//     accumulators in registers across the 4 k16-blocks of a tile and across the tiles of a quantisation
+//     group, folds zero-point / scale inside the warp (lane l owns word-column l: its 8 columns' scales
+//     are one LDS.128, their zeros one LDS.32) into a per-warp column accumulator in shared memory;
+//   * one CTA-level reduction at the end (or a warp-level push when a warp's run crosses a 256-column
+//     block), fp32 atomics into the zeroed workspace, tickets count TILES so the last contributor of a
+//     column block is known without any host-side schedule.
 namespace b200awq {
 
 constexpr int kV3TileRows = 64;
@@ -325,17 +330,70 @@ constexpr int kV3TileBytes = kV3TileRows * 128;               // 8 KB of packed 
 constexpr int kV3ScaleBytes = kV3TileCols * 2;                // 512 B
 constexpr int kV3ZeroBytes = kV3TileCols / 8 * 4;             // 128 B
 constexpr int kV3StageBytes = 9216;                           // 8192 + 640, padded to 1024 (swizzle atoms)
-constexpr int kV3Threads = 32 + 256;                          // producer warp + 2 x 4 consumer warps
+constexpr int kV3Warps = 8;                                   // consumer warps
+constexpr int kV3Threads = 32 + kV3Warps * 32;                // producer warp + consumers
 
 template <int MT>
 struct V3Smem {
-  static constexpr int kStages = MT <= 2 ? 16 : (MT == 4 ? 12 : 8);  // even: stage parity == group parity
-  static constexpr int red_floats = 2 * 4 * MT * kGvRedStride;       // [grp][warp4][MT][272]
-  static constexpr int colacc_floats = 2 * MT * kV3TileCols;         // [grp][MT][256]
-  static constexpr int xsum_floats = 2 * 4 * MT;                     // [grp][warp4][MT]
-  static constexpr size_t bytes = (size_t)kStages * kV3StageBytes + 1024 /*align*/ +
-                                  (size_t)(red_floats + colacc_floats + xsum_floats) * 4 + 2 * kStages * 8 + 64;
+  static constexpr int kStagesPerWarp = MT <= 4 ? 2 : 1;
+  static constexpr int kStages = kV3Warps * kStagesPerWarp;
+  static constexpr int red_floats = kV3Warps * MT * kGvRedStride;    // per-warp raw sums [MT][272]
+  static constexpr int colacc_floats = kV3Warps * MT * kV3TileCols;  // per-warp column sums [MT][256]
+  static constexpr size_t bytes = (size_t)kStages * kV3StageBytes + (size_t)(red_floats + colacc_floats) * 4 +
+                                  2 * kStages * 8 + 128;
 };
+
+// Shared by the warp-level (NT = 32) and CTA-level (NT = 256) pushes: add `cols` [MT][256] (shared memory,
+// summed over `nsrc` sources `src_stride` floats apart) into the fp32 workspace, count `ntl` tiles on the
+// column block's ticket and, if this was the last contribution, round to fp16 (+ bias) and re-zero.
+template <int MT, int NT>
+__device__ __forceinline__ void v3_push(float* cols, int nsrc, int src_stride, int cb, int ntl, int TPC, int t,
+                                        int* flag, const __half* __restrict__ bias, __half* __restrict__ y,
+                                        float* __restrict__ acc_ws, int* __restrict__ tickets, int M, int N) {
+  const int n_base = cb * kV3TileCols;
+  auto sync = [&]() {
+    if (NT == 32) __syncwarp(); else named_bar_sync_gv(1, NT);
+  };
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    if (m < M) {
+      for (int c = t; c < kV3TileCols; c += NT) {
+        float v = 0.f;
+        for (int sidx = 0; sidx < nsrc; ++sidx) {
+          v += cols[sidx * src_stride + m * kV3TileCols + c];
+          cols[sidx * src_stride + m * kV3TileCols + c] = 0.f;
+        }
+        atomicAdd(&acc_ws[(int64_t)m * N + n_base + c], v);
+      }
+    }
+  }
+  __threadfence();
+  sync();
+  if (t == 0) {
+    const int prev = atomicAdd(&tickets[cb], ntl);
+    *flag = (prev + ntl == TPC);
+  }
+  sync();
+  const bool last = *flag != 0;
+  sync();  // the flag may be rewritten by a later push
+  if (last) {
+    __threadfence();
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) {
+        for (int c = t; c < kV3TileCols; c += NT) {
+          const int n = n_base + c;
+          float* p = &acc_ws[(int64_t)m * N + n];
+          float v = ldcg_f1(p);
+          *p = 0.f;
+          if (bias != nullptr) v += __half2float(bias[n]);
+          y[(int64_t)m * N + n] = __float2half_rn(v);
+        }
+      }
+    }
+    if (t == 0) tickets[cb] = 0;
+  }
+}
 
 template <int MT>
 __global__ void __launch_bounds__(kV3Threads, 1)
@@ -343,16 +401,17 @@ __global__ void __launch_bounds__(kV3Threads, 1)
                    const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                    const __half* __restrict__ bias, __half* __restrict__ y, float* __restrict__ acc_ws,
                    int* __restrict__ tickets, int M, int K, int N, int G) {
-  constexpr int kV3Stages = V3Smem<MT>::kStages;
-  extern __shared__ uint8_t v3_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(v3_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem;
-  float* red = reinterpret_cast<float*>(smem + (size_t)kV3Stages * kV3StageBytes);
+  constexpr int SPW = V3Smem<MT>::kStagesPerWarp;
+  constexpr int NS = V3Smem<MT>::kStages;
+  extern __shared__ __align__(1024) uint8_t v3_smem[];
+  uint8_t* ring = v3_smem;
+  float* red = reinterpret_cast<float*>(v3_smem + (size_t)NS * kV3StageBytes);
   float* colacc = red + V3Smem<MT>::red_floats;
-  float* xsum_s = colacc + V3Smem<MT>::colacc_floats;
-  uint64_t* full = reinterpret_cast<uint64_t*>(xsum_s + V3Smem<MT>::xsum_floats);
-  uint64_t* empty = full + kV3Stages;
-  int* flags = reinterpret_cast<int*>(empty + kV3Stages);  // [2] last-contributor flags, one per group
+  uint64_t* full = reinterpret_cast<uint64_t*>(colacc + V3Smem<MT>::colacc_floats);
+  uint64_t* empty = full + NS;
+  int* flags = reinterpret_cast<int*>(empty + NS);   // [0..7] per-warp push flags, [8] CTA flag,
+  int* warp_cb = flags + 16;                         // [8] column block of each warp's pending sums
+  int* warp_ntl = warp_cb + 8;                       // [8] tiles those sums cover
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NW = N >> 3;
@@ -364,10 +423,11 @@ __global__ void __launch_bounds__(kV3Threads, 1)
 
   pdl_trigger();
   if (tid == 0) {
+    if ((smem_u32(v3_smem) & 1023u) != 0) __trap();  // the 128B-swizzle read pattern assumes 1 KB aligned stages
     tma_prefetch_desc(&tmw);
-    for (int s = 0; s < kV3Stages; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);  // one elected arrival by the group that consumed the stage
+      mbar_init(&empty[s], 1);
     }
     fence_mbar_init();
   }
@@ -376,12 +436,15 @@ __global__ void __launch_bounds__(kV3Threads, 1)
 
   if (warp == 0) {
     // ============================================================ producer: weights never wait for PDL
-    if (lane == 0) {
-      for (int i = 0; i < ntile; ++i) {
-        const int stage = i % kV3Stages;
-        const uint32_t ph = (uint32_t)(i / kV3Stages) & 1u;
+    // lane w feeds consumer warp w's private stages: no head-of-line blocking between consumers
+    if (lane < kV3Warps) {
+      const int w = lane;
+      const int a = t0 + (int)((int64_t)ntile * w / kV3Warps);
+      const int bnd = t0 + (int)((int64_t)ntile * (w + 1) / kV3Warps);
+      for (int t = a, j = 0; t < bnd; ++t, ++j) {
+        const int stage = w * SPW + (j % SPW);
+        const uint32_t ph = (uint32_t)(j / SPW) & 1u;
         mbar_wait(&empty[stage], ph ^ 1);
-        const int t = t0 + i;
         const int cb = t / TPC, kt = t - cb * TPC;
         const int grp_abs = (kt * kV3TileRows) / G;
         uint8_t* st = ring + (size_t)stage * kV3StageBytes;
@@ -395,108 +458,77 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     return;
   }
 
-  // ================================================================ consumers
+  // ================================================================ consumers (independent warps)
   const int cw = warp - 1;             // 0..7
-  const int grp = cw >> 2;             // consumer group: takes tiles i = grp, grp + 2, ...
-  const int w4 = cw & 3;               // k16-block of the tile owned by this warp
-  const int gt = tid - 32 - grp * 128; // thread index inside the group, 0..127
+  const int ct = tid - 32;             // 0..255
   const int g = lane >> 2, tig = lane & 3;
   const bool tok_ok = g < M;
-  float* my_red = red + (size_t)(grp * 4 + w4) * MT * kGvRedStride;
-  float* grp_red = red + (size_t)(grp * 4) * MT * kGvRedStride;
-  float* my_col = colacc + (size_t)grp * MT * kV3TileCols;
-  float* grp_xsum = xsum_s + grp * 4 * MT;
+  float* my_red = red + (size_t)cw * MT * kGvRedStride;
+  float* my_col = colacc + (size_t)cw * MT * kV3TileCols;
+  const int a_w = t0 + (int)((int64_t)ntile * cw / kV3Warps);
+  const int b_w = t0 + (int)((int64_t)ntile * (cw + 1) / kV3Warps);
 
   pdl_wait();  // activations, workspace, tickets, outputs belong to the stream order
 
-  int cur_cb = -1, tiles_in_cb = 0;
-  auto push = [&](int cb, int ntl) {
-    // column sums of this group -> fp32 workspace; tickets count tiles; last contributor finalises
-    const int n_base = cb * kV3TileCols;
+  // activations of tile t, block b: rows 16b + {2tig, 2tig+1} and 16b + {2tig+8, 2tig+9}
+  auto load_x = [&](int t, uint32_t (&xb)[4][2]) {
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      if (m < M) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c = gt + 128 * h;
-          atomicAdd(&acc_ws[(int64_t)m * N + n_base + c], my_col[m * kV3TileCols + c]);
-          my_col[m * kV3TileCols + c] = 0.f;
-        }
-      }
-    }
-    __threadfence();
-    named_bar_sync_gv(1 + grp, 128);
-    if (gt == 0) {
-      const int prev = atomicAdd(&tickets[cb], ntl);
-      flags[grp] = (prev + ntl == TPC);
-    }
-    named_bar_sync_gv(1 + grp, 128);
-    if (flags[grp]) {
-      __threadfence();
-#pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        if (m < M) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int n = n_base + gt + 128 * h;
-            float* p = &acc_ws[(int64_t)m * N + n];
-            float v = ldcg_f1(p);
-            *p = 0.f;
-            if (bias != nullptr) v += __half2float(bias[n]);
-            y[(int64_t)m * N + n] = __float2half_rn(v);
-          }
-        }
-      }
-      if (gt == 0) tickets[cb] = 0;
-    }
-    named_bar_sync_gv(1 + grp, 128);  // flags[grp] may be rewritten by the next push
-  };
-
-  // activations of this warp's block of tile i: rows 2tig, 2tig+1 and 2tig+8, 2tig+9 of the k16-block
-  auto load_x = [&](int i, uint32_t& b0, uint32_t& b1) {
-    b0 = b1 = 0u;
-    if (i < ntile && tok_ok) {
-      const int t = t0 + i;
+    for (int bb = 0; bb < 4; ++bb) xb[bb][0] = xb[bb][1] = 0u;
+    if (t < b_w && tok_ok) {
       const int kt = t % TPC;
-      const __half* px = x + (int64_t)g * ldx + kt * kV3TileRows + 16 * w4 + 2 * tig;
-      b0 = *reinterpret_cast<const uint32_t*>(px);
-      b1 = *reinterpret_cast<const uint32_t*>(px + 8);
+      const __half* px = x + (int64_t)g * ldx + kt * kV3TileRows + 2 * tig;
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        xb[bb][0] = *reinterpret_cast<const uint32_t*>(px + 16 * bb);
+        xb[bb][1] = *reinterpret_cast<const uint32_t*>(px + 16 * bb + 8);
+      }
     }
   };
-  uint32_t xb0, xb1, nxb0, nxb1;
-  load_x(grp, xb0, xb1);
 
-  for (int i = grp; i < ntile; i += 2) {
-    const int stage = i % kV3Stages;
-    const uint32_t ph = (uint32_t)(i / kV3Stages) & 1u;
-    const int t = t0 + i;
-    const int cb = t / TPC;
-    if (cb != cur_cb) {
-      if (cur_cb >= 0) push(cur_cb, tiles_in_cb);
-      cur_cb = cb;
-      tiles_in_cb = 0;
-    }
-    ++tiles_in_cb;
-    load_x(i + 2, nxb0, nxb1);  // next tile's activations in flight while this one is computed
-    mbar_wait(&full[stage], ph);
-    const uint8_t* st = ring + (size_t)stage * kV3StageBytes;
-
-    // ---- fragments from the swizzled tile: rows (2tig, 2tig+1, 2tig+8, 2tig+9) of block w4, chunk g
-    const int r0 = 16 * w4 + 2 * tig;
-    const uint4 qa = *reinterpret_cast<const uint4*>(st + (r0 + 0) * 128 + ((g ^ ((r0 + 0) & 7)) << 4));
-    const uint4 qb = *reinterpret_cast<const uint4*>(st + (r0 + 1) * 128 + ((g ^ ((r0 + 1) & 7)) << 4));
-    const uint4 qc = *reinterpret_cast<const uint4*>(st + (r0 + 8) * 128 + ((g ^ ((r0 + 8) & 7)) << 4));
-    const uint4 qd = *reinterpret_cast<const uint4*>(st + (r0 + 9) * 128 + ((g ^ ((r0 + 9) & 7)) << 4));
-    float acc[4][4][4];
-    float xs_acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[4][4][4];
+  float xs_acc[4];
+  auto zero_acc = [&]() {
 #pragma unroll
     for (int w = 0; w < 4; ++w)
 #pragma unroll
       for (int tt = 0; tt < 4; ++tt)
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[w][tt][r] = 0.f;
-    {
+    xs_acc[0] = xs_acc[1] = xs_acc[2] = xs_acc[3] = 0.f;
+  };
+  zero_acc();
+
+  int cur_cb = -1, ntl = 0;
+  uint32_t xcur[4][2], xnext[4][2];
+  load_x(a_w, xcur);
+  for (int t = a_w, j = 0; t < b_w; ++t, ++j) {
+    const int stage = cw * SPW + (j % SPW);
+    const uint32_t ph = (uint32_t)(j / SPW) & 1u;
+    const int cb = t / TPC, kt = t - cb * TPC;
+    if (cb != cur_cb) {
+      if (cur_cb >= 0 && ntl > 0) {
+        // this warp's run crosses a column block: push its pending sums alone (rare)
+        __syncwarp();
+        v3_push<MT, 32>(my_col, 1, 0, cur_cb, ntl, TPC, lane, &flags[cw], bias, y, acc_ws, tickets, M, N);
+      }
+      cur_cb = cb;
+      ntl = 0;
+    }
+    ++ntl;
+    load_x(t + 1, xnext);  // next tile's activations in flight while this one is computed
+    mbar_wait(&full[stage], ph);
+    const uint8_t* st = ring + (size_t)stage * kV3StageBytes;
+
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      // fragments from the swizzled tile: rows (2tig, 2tig+1, 2tig+8, 2tig+9) of block bb, 16-byte chunk g
+      const int r0 = 16 * bb + 2 * tig;
+      const uint4 qa = *reinterpret_cast<const uint4*>(st + (r0 + 0) * 128 + ((g ^ ((r0 + 0) & 7)) << 4));
+      const uint4 qb = *reinterpret_cast<const uint4*>(st + (r0 + 1) * 128 + ((g ^ ((r0 + 1) & 7)) << 4));
+      const uint4 qc = *reinterpret_cast<const uint4*>(st + (r0 + 8) * 128 + ((g ^ ((r0 + 8) & 7)) << 4));
+      const uint4 qd = *reinterpret_cast<const uint4*>(st + (r0 + 9) * 128 + ((g ^ ((r0 + 9) & 7)) << 4));
       constexpr uint32_t MA = 0x000f000fu, MB = 0x00f000f0u, MG = 0x64006400u, ONES = 0x3C003C00u;
+      const uint32_t xb0 = xcur[bb][0], xb1 = xcur[bb][1];
       mma_16816(xs_acc, ONES, ONES, ONES, ONES, xb0, xb1);
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
@@ -514,57 +546,98 @@ __global__ void __launch_bounds__(kV3Threads, 1)
                   lop3_and_or(hi23s, MB, MG), xb0, xb1);
       }
     }
-    // ---- raw sums of this warp -> shared memory
-#pragma unroll
-    for (int w = 0; w < 4; ++w)
-#pragma unroll
-      for (int tt = 0; tt < 4; ++tt) {
-        const int pc = gv_pos(32 * g + 8 * w + 2 * tt);
-        if (2 * tig < MT)
-          *reinterpret_cast<float2*>(&my_red[(2 * tig) * kGvRedStride + pc]) = make_float2(acc[w][tt][0], acc[w][tt][2]);
-        if (2 * tig + 1 < MT)
-          *reinterpret_cast<float2*>(&my_red[(2 * tig + 1) * kGvRedStride + pc]) =
-              make_float2(acc[w][tt][1], acc[w][tt][3]);
-      }
-    if (g == 0) {
-      if (2 * tig < MT) grp_xsum[w4 * MT + 2 * tig] = xs_acc[0];
-      if (2 * tig + 1 < MT) grp_xsum[w4 * MT + 2 * tig + 1] = xs_acc[1];
-    }
-    named_bar_sync_gv(1 + grp, 128);
 
-    // ---- fold (one group = one tile = one quantisation group): thread gt owns columns gt and gt + 128
-    {
-      const __half* s_sc = reinterpret_cast<const __half*>(st + kV3TileBytes);
-      const uint32_t* s_z = reinterpret_cast<const uint32_t*>(st + kV3TileBytes + kV3ScaleBytes);
+    // ---- fold when the quantisation group (or this warp's run) ends with this tile -----------------
+    const bool group_end = (((kt + 1) * kV3TileRows) % G) == 0;
+    if (group_end || t + 1 == b_w) {
+      // raw sums -> this warp's staging area (conflict-free float2 stores), then lane l folds word-column l
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+          const int pc = gv_pos(32 * g + 8 * w + 2 * tt);
+          if (2 * tig < MT)
+            *reinterpret_cast<float2*>(&my_red[(2 * tig) * kGvRedStride + pc]) = make_float2(acc[w][tt][0], acc[w][tt][2]);
+          if (2 * tig + 1 < MT)
+            *reinterpret_cast<float2*>(&my_red[(2 * tig + 1) * kGvRedStride + pc]) =
+                make_float2(acc[w][tt][1], acc[w][tt][3]);
+        }
+      // sum_k x_k per token: d0 / d1 of the ones-row MMA live in the tig lanes of every g; take g = 0
       float X[MT];
 #pragma unroll
-      for (int m = 0; m < MT; ++m)
-        X[m] = grp_xsum[0 * MT + m] + grp_xsum[1 * MT + m] + grp_xsum[2 * MT + m] + grp_xsum[3 * MT + m];
+      for (int m = 0; m < MT; ++m) {
+        const float v = (m & 1) ? xs_acc[1] : xs_acc[0];
+        X[m] = __shfl_sync(0xffffffffu, v, m >> 1);  // lane (g = 0, tig = m / 2)
+      }
+      __syncwarp();
+      {
+        const uint4 sc4 = *reinterpret_cast<const uint4*>(st + kV3TileBytes + lane * 16);            // 8 scales
+        const uint32_t zw = *reinterpret_cast<const uint32_t*>(st + kV3TileBytes + kV3ScaleBytes + lane * 4);
+        const __half2* sc2 = reinterpret_cast<const __half2*>(&sc4);
+        float sc[8], zoff[8];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = gt + 128 * h;
-        const int j = c & 7;
-        const bool kindB = ((j >> 1) & 1) != 0;
-        const int zshift = 4 * ((j >> 1) + 4 * (j & 1));
-        float sc = __half2float(s_sc[c]);
-        const float z = static_cast<float>((s_z[c >> 3] >> zshift) & 0xFu);
-        const float zoff = kindB ? 1024.f + 16.f * z : 1024.f + z;
-        if (kindB) sc *= 0.0625f;
-        const int pc = gv_pos(c);
+        for (int jj = 0; jj < 4; ++jj) {
+          const float2 f = __half22float2(sc2[jj]);
+          sc[2 * jj] = f.x;
+          sc[2 * jj + 1] = f.y;
+        }
+#pragma unroll
+        for (int jc = 0; jc < 8; ++jc) {
+          const int zshift = 4 * ((jc >> 1) + 4 * (jc & 1));  // 4 * AWQ_REVERSE_ORDER[jc]
+          const float z = static_cast<float>((zw >> zshift) & 0xFu);
+          const bool kindB = ((jc >> 1) & 1) != 0;
+          zoff[jc] = kindB ? 1024.f + 16.f * z : 1024.f + z;
+          if (kindB) sc[jc] *= 0.0625f;
+        }
+        const int pc0 = gv_pos(8 * lane);  // 8 consecutive floats (never straddles a pad)
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-          const float S = grp_red[(0 * MT + m) * kGvRedStride + pc] + grp_red[(1 * MT + m) * kGvRedStride + pc] +
-                          grp_red[(2 * MT + m) * kGvRedStride + pc] + grp_red[(3 * MT + m) * kGvRedStride + pc];
-          my_col[m * kV3TileCols + c] += sc * (S - zoff * X[m]);
+          const float4 s0 = *reinterpret_cast<const float4*>(&my_red[m * kGvRedStride + pc0]);
+          const float4 s1 = *reinterpret_cast<const float4*>(&my_red[m * kGvRedStride + pc0 + 4]);
+          float4* c0 = reinterpret_cast<float4*>(&my_col[m * kV3TileCols + 8 * lane]);
+          float4 a0 = c0[0], a1 = c0[1];
+          a0.x += sc[0] * (s0.x - zoff[0] * X[m]);
+          a0.y += sc[1] * (s0.y - zoff[1] * X[m]);
+          a0.z += sc[2] * (s0.z - zoff[2] * X[m]);
+          a0.w += sc[3] * (s0.w - zoff[3] * X[m]);
+          a1.x += sc[4] * (s1.x - zoff[4] * X[m]);
+          a1.y += sc[5] * (s1.y - zoff[5] * X[m]);
+          a1.z += sc[6] * (s1.z - zoff[6] * X[m]);
+          a1.w += sc[7] * (s1.w - zoff[7] * X[m]);
+          c0[0] = a0;
+          c0[1] = a1;
         }
       }
+      zero_acc();
     }
-    named_bar_sync_gv(1 + grp, 128);       // all reads of the stage and of red[] are done
-    if (gt == 0) mbar_arrive(&empty[stage]);
-    xb0 = nxb0;
-    xb1 = nxb1;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);   // the whole warp is done reading this stage
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) {
+      xcur[bb][0] = xnext[bb][0];
+      xcur[bb][1] = xnext[bb][1];
+    }
   }
-  if (cur_cb >= 0) push(cur_cb, tiles_in_cb);
+
+  // ---- CTA-level reduction of the per-warp column sums, grouped by column block --------------------
+  if (lane == 0) {
+    warp_cb[cw] = (ntl > 0) ? cur_cb : -1;
+    warp_ntl[cw] = ntl;
+  }
+  named_bar_sync_gv(1, kV3Warps * 32);
+  int w0 = 0;
+  while (w0 < kV3Warps) {
+    const int cb = warp_cb[w0];
+    int w1 = w0 + 1, tiles = warp_ntl[w0];
+    while (w1 < kV3Warps && warp_cb[w1] == cb) {
+      tiles += warp_ntl[w1];
+      ++w1;
+    }
+    if (cb >= 0)
+      v3_push<MT, kV3Warps * 32>(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cb, tiles, TPC, ct,
+                                 &flags[8], bias, y, acc_ws, tickets, M, N);
+    w0 = w1;
+  }
 }
 
 static int v3_sm_count() {
