@@ -11,7 +11,7 @@
 //   D         = [128 lanes (n) x BT columns (tokens)] fp32 in tensor memory.
 // Warp roles (448 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
 // warps 2..5 = epilogue (tcgen05.ld -> +bias -> fp16 -> global), warps 6..13 = dequant producers.
-// Pipeline: NS smem stages, one "full" mbarrier per stage (256 dequant arrivals + 1 TMA expect_tx),
+// Pipeline: NS smem stages, one "full" mbarrier per stage (8 producer-warp arrivals + 1 TMA expect_tx),
 // one "empty" mbarrier per stage (tcgen05.commit); two TMEM accumulator buffers with tmem_full /
 // tmem_empty mbarriers, so the epilogue of one tile overlaps the main loop of the next.
 // Persistent CTAs walk (n_tile, m_tile, k_split) work items.  Split-K (only for M <= 64, where the
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmx);
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], kProducers + 1);
+      mbar_init(&full[s], kProducers / 32 + 1);  // one elected arrival per producer warp + the TMA expect_tx
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -422,8 +422,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           if (s < s_end) {
             mbar_wait(&empty[stage], phase ^ 1);
             ring[d].store(p, nt, s * kBK, dt, a_base + (size_t)stage * kAStageBytes);
-            fence_proxy_async_smem();
-            mbar_arrive(&full[stage]);
+            fence_proxy_async_smem();   // every writer: generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);  // 8 arrivals per stage instead of 256
             if (++stage == NS) { stage = 0; phase ^= 1; }
             if (s + kPrefetch < s_end) ring[d].load(p, nt, (s + kPrefetch) * kBK, dt);
           }

@@ -329,18 +329,20 @@ constexpr int kV3TileCols = 256;
 constexpr int kV3TileBytes = kV3TileRows * 128;               // 8 KB of packed weights
 constexpr int kV3ScaleBytes = kV3TileCols * 2;                // 512 B
 constexpr int kV3ZeroBytes = kV3TileCols / 8 * 4;             // 128 B
-constexpr int kV3StageBytes = 9216;                           // 8192 + 640, padded to 1024 (swizzle atoms)
+constexpr int kV3AuxBytes = kV3ScaleBytes + kV3ZeroBytes;     // 640 B of group constants per stage
 constexpr int kV3Warps = 8;                                   // consumer warps
 constexpr int kV3Threads = 32 + kV3Warps * 32;                // producer warp + consumers
 
 template <int MT>
 struct V3Smem {
-  static constexpr int kStagesPerWarp = MT <= 4 ? 2 : 1;
+  // bytes in flight are what buys bandwidth (HBM latency under load is several us): as many 8 KB stages
+  // per consumer warp as the 227 KB of shared memory allow next to the per-warp reduction buffers
+  static constexpr int kStagesPerWarp = MT == 1 ? 3 : (MT <= 4 ? 2 : 1);
   static constexpr int kStages = kV3Warps * kStagesPerWarp;
-  static constexpr int red_floats = kV3Warps * MT * kGvRedStride;    // per-warp raw sums [MT][272]
+  static constexpr int red_floats = kV3Warps * MT * kGvRedStride;    // per-warp raw sums [MT][288]
   static constexpr int colacc_floats = kV3Warps * MT * kV3TileCols;  // per-warp column sums [MT][256]
-  static constexpr size_t bytes = (size_t)kStages * kV3StageBytes + (size_t)(red_floats + colacc_floats) * 4 +
-                                  2 * kStages * 8 + 128;
+  static constexpr size_t bytes = (size_t)kStages * (kV3TileBytes + kV3AuxBytes) +
+                                  (size_t)(red_floats + colacc_floats) * 4 + 2 * kStages * 8 + 128;
 };
 
 // Shared by the warp-level (NT = 32) and CTA-level (NT = 256) pushes: add `cols` [MT][256] (shared memory,
@@ -404,8 +406,9 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   constexpr int SPW = V3Smem<MT>::kStagesPerWarp;
   constexpr int NS = V3Smem<MT>::kStages;
   extern __shared__ __align__(1024) uint8_t v3_smem[];
-  uint8_t* ring = v3_smem;
-  float* red = reinterpret_cast<float*>(v3_smem + (size_t)NS * kV3StageBytes);
+  uint8_t* ring = v3_smem;                                   // NS x 8 KB weight tiles (1 KB aligned: swizzle atoms)
+  uint8_t* aux = v3_smem + (size_t)NS * kV3TileBytes;        // NS x (256 scales + 32 zero words)
+  float* red = reinterpret_cast<float*>(aux + (size_t)NS * kV3AuxBytes);
   float* colacc = red + V3Smem<MT>::red_floats;
   uint64_t* full = reinterpret_cast<uint64_t*>(colacc + V3Smem<MT>::colacc_floats);
   uint64_t* empty = full + NS;
@@ -447,12 +450,13 @@ __global__ void __launch_bounds__(kV3Threads, 1)
         mbar_wait(&empty[stage], ph ^ 1);
         const int cb = t / TPC, kt = t - cb * TPC;
         const int grp_abs = (kt * kV3TileRows) / G;
-        uint8_t* st = ring + (size_t)stage * kV3StageBytes;
-        mbar_arrive_expect_tx(&full[stage], kV3TileBytes + kV3ScaleBytes + kV3ZeroBytes);
+        uint8_t* st = ring + (size_t)stage * kV3TileBytes;
+        uint8_t* sa = aux + (size_t)stage * kV3AuxBytes;
+        mbar_arrive_expect_tx(&full[stage], kV3TileBytes + kV3AuxBytes);
         tma_load_2d(st, &tmw, &full[stage], cb * (kV3TileCols / 8), kt * kV3TileRows);
-        bulk_load_1d(st + kV3TileBytes, scales + (int64_t)grp_abs * N + cb * kV3TileCols, kV3ScaleBytes, &full[stage]);
-        bulk_load_1d(st + kV3TileBytes + kV3ScaleBytes, qzeros + (int64_t)grp_abs * NW + cb * (kV3TileCols / 8),
-                     kV3ZeroBytes, &full[stage]);
+        bulk_load_1d(sa, scales + (int64_t)grp_abs * N + cb * kV3TileCols, kV3ScaleBytes, &full[stage]);
+        bulk_load_1d(sa + kV3ScaleBytes, qzeros + (int64_t)grp_abs * NW + cb * (kV3TileCols / 8), kV3ZeroBytes,
+                     &full[stage]);
       }
     }
     return;
@@ -517,7 +521,8 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     ++ntl;
     load_x(t + 1, xnext);  // next tile's activations in flight while this one is computed
     mbar_wait(&full[stage], ph);
-    const uint8_t* st = ring + (size_t)stage * kV3StageBytes;
+    const uint8_t* st = ring + (size_t)stage * kV3TileBytes;
+    const uint8_t* sa = aux + (size_t)stage * kV3AuxBytes;
 
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) {
@@ -571,8 +576,8 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       }
       __syncwarp();
       {
-        const uint4 sc4 = *reinterpret_cast<const uint4*>(st + kV3TileBytes + lane * 16);            // 8 scales
-        const uint32_t zw = *reinterpret_cast<const uint32_t*>(st + kV3TileBytes + kV3ScaleBytes + lane * 4);
+        const uint4 sc4 = *reinterpret_cast<const uint4*>(sa + lane * 16);            // 8 scales
+        const uint32_t zw = *reinterpret_cast<const uint32_t*>(sa + kV3ScaleBytes + lane * 4);
         const __half2* sc2 = reinterpret_cast<const __half2*>(&sc4);
         float sc[8], zoff[8];
 #pragma unroll

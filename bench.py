@@ -308,7 +308,7 @@ def main():
         ach = alg_bytes / n_lin / avg_launch_s / 1e9
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
-                "kernel": "gemv_gemm_layout_kernel<4,1,16,8,16>", "peak_src": peaks["src"] + " (hbm_gbs)",
+                "kernel": "gemv_v3_kernel<1> (persistent TMA-ring GEMV)", "peak_src": peaks["src"] + " (hbm_gbs)",
                 "per_launch": {"avg_us": round(avg_launch_s * 1e6, 2), "alg_bytes": alg_bytes // n_lin,
                                "launches_timed": n_lin * a.steps,
                                "how": "CUDA events around a graph of the 128 linear launches of one step"}}
