@@ -42,7 +42,7 @@ struct TcParams {
   int M, K, N, G;
   int zw;          // GEMV layout: zeros width
   int n_tiles, m_tiles, ksplit;
-  int a_desc_variant;
+  int has_tmq;     // GEMM layout: a tensor map over qweight is available for L2 prefetch
 };
 
 template <int BT>
@@ -234,7 +234,8 @@ constexpr int kTcThreads = 64 + 128 + kProducers;
 
 template <int BT, int LAYOUT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmx, const TcParams p) {
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
+                   const TcParams p) {
   using Cfg = TcCfg<BT>;
   constexpr int NS = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -280,6 +281,27 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 0) {
     // ================================================================= TMA producer (X tiles)
     if (lane == 0) {
+      // GEMM layout: pull the packed weights of the next kL2Ahead k-steps from HBM into L2 (TMA prefetch, no
+      // smem destination) so that the producers' register prefetch only has to cover L2 latency.  Weights
+      // do not depend on the predecessor kernel: this starts before the PDL wait.
+      constexpr int kL2Ahead = 16;
+      int wp = blockIdx.x, sp = 0, sp_end = 0;
+      bool pf_valid = (LAYOUT == 0) && p.has_tmq && wp < n_work;
+      auto pf_range = [&]() {
+        const int ks = wp % p.ksplit;
+        sp = (int)((int64_t)KS * ks / p.ksplit);
+        sp_end = (int)((int64_t)KS * (ks + 1) / p.ksplit);
+      };
+      auto pf_step = [&]() {
+        const int nt = wp / (p.ksplit * p.m_tiles);
+        tma_prefetch_l2_2d(&tmq, nt * 16, sp * kBK);
+        if (++sp == sp_end) {
+          wp += gridDim.x;
+          if (wp < n_work) pf_range(); else pf_valid = false;
+        }
+      };
+      if (pf_valid) pf_range();
+      for (int i = 0; i < kL2Ahead && pf_valid; ++i) pf_step();
       pdl_wait();  // the activations are the predecessor's output
       int stage = 0;
       uint32_t phase = 0;
@@ -292,6 +314,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           mbar_arrive_expect_tx(&full[stage], Cfg::kXStageBytes);
           tma_load_2d(x_base + (size_t)stage * Cfg::kXStageBytes, &tmx, &full[stage], s * kBK, mt * BT);
           if (++stage == NS) { stage = 0; phase ^= 1; }
+          if (pf_valid) pf_step();
         }
       }
     }
@@ -462,7 +485,7 @@ struct TmapKey {
   const void* ptr;
   uint64_t inner, outer, pitch;
   uint32_t bi, bo;
-  int kind;
+  int kind;  // bit 0: element type, bit 1: 128B swizzle
   bool operator==(const TmapKey& o) const {
     return ptr == o.ptr && inner == o.inner && outer == o.outer && pitch == o.pitch && bi == o.bi && bo == o.bo &&
            kind == o.kind;
@@ -478,10 +501,10 @@ struct TmapKeyHash {
 };
 
 cudaError_t make_tmap_2d(const void* ptr, int elem_kind, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-                         uint32_t box_inner, uint32_t box_outer, CUtensorMap* out) {
+                         uint32_t box_inner, uint32_t box_outer, CUtensorMap* out, bool swizzle128) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{ptr, inner, outer, pitch_bytes, box_inner, box_outer, elem_kind};
+  TmapKey key{ptr, inner, outer, pitch_bytes, box_inner, box_outer, elem_kind | (swizzle128 ? 2 : 0)};
   {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
@@ -498,7 +521,8 @@ cudaError_t make_tmap_2d(const void* ptr, int elem_kind, uint64_t inner, uint64_
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = elem_kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_INT32;
   CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
   std::lock_guard<std::mutex> lk(mu);
   if (cache.size() > 8192) cache.clear();
@@ -523,7 +547,7 @@ static int sm_count() {
 }
 
 template <int BT, int LAYOUT>
-static cudaError_t launch_tc(const CUtensorMap& tm, const TcParams& p, cudaStream_t st) {
+static cudaError_t launch_tc(const CUtensorMap& tm, const CUtensorMap& tmq, const TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BT>;
   auto kern = gemm_tc_kernel<BT, LAYOUT>;
   static bool attr_set[64] = {};
@@ -536,16 +560,17 @@ static cudaError_t launch_tc(const CUtensorMap& tm, const TcParams& p, cudaStrea
   }
   const int n_work = p.n_tiles * p.m_tiles * p.ksplit;
   const int grid = n_work < sm_count() ? n_work : sm_count();
-  return launch_kernel(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, st, tm, p);
+  return launch_kernel(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, st, tm, tmq, p);
 }
 
 template <int LAYOUT>
-static cudaError_t dispatch_bt(int BT, const CUtensorMap& tm, const TcParams& p, cudaStream_t st) {
+static cudaError_t dispatch_bt(int BT, const CUtensorMap& tm, const CUtensorMap& tmq, const TcParams& p,
+                               cudaStream_t st) {
   switch (BT) {
-    case 32: return launch_tc<32, LAYOUT>(tm, p, st);
-    case 64: return launch_tc<64, LAYOUT>(tm, p, st);
-    case 128: return launch_tc<128, LAYOUT>(tm, p, st);
-    default: return launch_tc<256, LAYOUT>(tm, p, st);
+    case 32: return launch_tc<32, LAYOUT>(tm, tmq, p, st);
+    case 64: return launch_tc<64, LAYOUT>(tm, tmq, p, st);
+    case 128: return launch_tc<128, LAYOUT>(tm, tmq, p, st);
+    default: return launch_tc<256, LAYOUT>(tm, tmq, p, st);
   }
 }
 
@@ -571,7 +596,6 @@ cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, 
   p.zw = zeros_width_tc(a.K, a.G);
   p.n_tiles = (a.N + kTileN - 1) / kTileN;
   p.m_tiles = (a.M + BT - 1) / BT;
-  p.a_desc_variant = knob(3);
   const int KS = a.K / kBK;
   int ksplit = 1;
   const int tiles = p.n_tiles * p.m_tiles;
@@ -583,13 +607,21 @@ cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, 
   const int forced = knob(1);
   if (forced > 0 && a.M <= kMaxSplitM && acc_ws != nullptr && tickets != nullptr) ksplit = forced > KS ? KS : forced;
   p.ksplit = ksplit;
-  CUtensorMap tm;
+  CUtensorMap tm, tmq;
   cudaError_t e = make_x_tmap(a.x, a.ldx, a.M, a.K, BT, &tm);
   if (e != cudaSuccess) return e;
+  tmq = tm;
+  p.has_tmq = 0;
+  if (layout == 0 && (a.N % 4) == 0 && (reinterpret_cast<uintptr_t>(a.qweight) & 15) == 0 && (a.N / 8) % 4 == 0) {
+    // qweight [K, N/8] int32 -> box {16 words = one 128-column tile, 64 rows}; only used for L2 prefetch
+    if (make_tmap_2d(a.qweight, 1, (uint64_t)(a.N / 8), (uint64_t)a.K, (uint64_t)(a.N / 8) * 4, 16, kBK, &tmq, false) ==
+        cudaSuccess)
+      p.has_tmq = 1;
+  }
   switch (layout) {
-    case 0: return dispatch_bt<0>(BT, tm, p, st);
-    case 1: return dispatch_bt<1>(BT, tm, p, st);
-    default: return dispatch_bt<2>(BT, tm, p, st);
+    case 0: return dispatch_bt<0>(BT, tm, tmq, p, st);
+    case 1: return dispatch_bt<1>(BT, tm, tmq, p, st);
+    default: return dispatch_bt<2>(BT, tm, tmq, p, st);
   }
 }
 

@@ -444,9 +444,18 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       const int w = lane;
       const int a = t0 + (int)((int64_t)ntile * w / kV3Warps);
       const int bnd = t0 + (int)((int64_t)ntile * (w + 1) / kV3Warps);
+      // HBM -> L2 prefetch runs kL2Ahead tiles ahead of the shared-memory ring: the ring (bounded by the
+      // 227 KB of shared memory) then only has to cover L2 latency, while ~0.5 MB per SM is in flight to L2.
+      constexpr int kL2Ahead = SPW + 6;
+      for (int tp = a; tp < bnd && tp < a + kL2Ahead; ++tp)
+        tma_prefetch_l2_2d(&tmw, (tp / TPC) * (kV3TileCols / 8), (tp % TPC) * kV3TileRows);
       for (int t = a, j = 0; t < bnd; ++t, ++j) {
         const int stage = w * SPW + (j % SPW);
         const uint32_t ph = (uint32_t)(j / SPW) & 1u;
+        if (t + kL2Ahead < bnd) {
+          const int tp = t + kL2Ahead;
+          tma_prefetch_l2_2d(&tmw, (tp / TPC) * (kV3TileCols / 8), (tp % TPC) * kV3TileRows);
+        }
         mbar_wait(&empty[stage], ph ^ 1);
         const int cb = t / TPC, kt = t - cb * TPC;
         const int grp_abs = (kt * kV3TileRows) / G;

@@ -61,7 +61,7 @@ cudaError_t dequantize_gemm(const int32_t* qweight, const void* scales, const in
 // 2-D tiled tensor map over a row-major matrix (cached by address + shape; weights are static, activations
 // recycle a few buffers).  elem_kind: 0 = fp16, 1 = int32.  128B swizzle, zero fill out of bounds.
 cudaError_t make_tmap_2d(const void* ptr, int elem_kind, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-                         uint32_t box_inner, uint32_t box_outer, CUtensorMap* out);
+                         uint32_t box_inner, uint32_t box_outer, CUtensorMap* out, bool swizzle128 = true);
 
 bool gemv_gemm_layout_supported(const GemmArgs& a);
 bool gemv_v3_supported(const GemmArgs& a);
