@@ -10,7 +10,7 @@
 //   B operand = X tile [BT tokens x 64 k], K-major, 128B swizzle, loaded by TMA (cp.async.bulk.tensor.2d).
 //   D         = [128 lanes (n) x BT columns (tokens)] fp32 in tensor memory.
 // Warp roles (448 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> +bias -> fp16 -> global), warps 6..13 = dequant producers.
+// warps 2..5 = epilogue (tcgen05.ld -> +bias -> fp16 -> global), warps 6.. = dequant producers (16 for the GEMM layout).
 // Pipeline: NS smem stages, one "full" mbarrier per stage (8 producer-warp arrivals + 1 TMA expect_tx),
 // one "empty" mbarrier per stage (tcgen05.commit); two TMEM accumulator buffers with tmem_full /
 // tmem_empty mbarriers, so the epilogue of one tile overlaps the main loop of the next.
@@ -59,37 +59,34 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // ------------------------------------------------------------------------------- A-tile producers
-// 256 producer threads (8 warps).  load() issues the global loads of one k-step (packed words plus,
+// 256 or 512 producer threads.  load() issues the global loads of one k-step (packed words plus,
 // when the quantisation group changes, the group's zeros / scales) ONE STEP AHEAD of store(), which
 // dequantises from registers and writes the swizzled fp16 tile: no global latency on the critical path.
-constexpr int kProducers = 256;
 
-// GEMM layout: thread dt owns word column c = dt % 16 (8 n) and rows kk = dt/16 + 16 j, j = 0..3.
+// GEMM layout, 512 producer threads: thread dt owns word column c = dt % 16 (8 n) and rows kk = dt/16 + 32 j,
+// j = 0, 1 (row halves of the 64-row step, which are also the two quantisation groups when G == 32).
 struct GemmLayoutLoader {
-  uint32_t q[4];
+  static constexpr int kThreads = 512;
+  uint32_t q[2];
   uint32_t zq[2];
   uint4 sc[2];
   int gidx[2];
   __device__ __forceinline__ void init() { gidx[0] = gidx[1] = -1; zq[0] = zq[1] = 0; sc[0] = sc[1] = make_uint4(0, 0, 0, 0); }
   __device__ __forceinline__ void load(const TcParams& p, int nt, int k0, int dt) {
     const int NW = p.N >> 3;
-    const int c = dt & 15, rb = dt >> 4;
+    const int c = dt & 15, rb = dt >> 4;  // rb = 0..31
     const int wc = nt * 16 + c;
     const bool ok = wc < NW;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 2; ++j) {
       q[j] = 0u;
-      if (ok) q[j] = ldg_stream_u1(p.qweight + (int64_t)(k0 + rb + 16 * j) * NW + wc);
-    }
-    // rows j = 0,1 (< 32) and j = 2,3 (>= 32) may sit in different groups when G == 32
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int g = (k0 + rb + 32 * h) / p.G;
-      if (g != gidx[h]) {
-        gidx[h] = g;
+      if (ok) q[j] = ldg_stream_u1(p.qweight + (int64_t)(k0 + rb + 32 * j) * NW + wc);
+      const int g = (k0 + rb + 32 * j) / p.G;
+      if (g != gidx[j]) {
+        gidx[j] = g;
         if (ok) {
-          zq[h] = static_cast<uint32_t>(__ldg(p.qzeros + (int64_t)g * NW + wc));
-          sc[h] = __ldg(reinterpret_cast<const uint4*>(p.scales + (int64_t)g * p.N + wc * 8));
+          zq[j] = static_cast<uint32_t>(__ldg(p.qzeros + (int64_t)g * NW + wc));
+          sc[j] = __ldg(reinterpret_cast<const uint4*>(p.scales + (int64_t)g * p.N + wc * 8));
         }
       }
     }
@@ -98,24 +95,21 @@ struct GemmLayoutLoader {
     const int c = dt & 15, rb = dt >> 4;
     const bool ok = (nt * 16 + c) < (p.N >> 3);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const ZeroPairs zp = awq_zero_pairs(zq[h]);
-#pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j = 2 * h + jj;
-        uint4 o = awq_dequant_word(q[j], zp, sc[h]);
-        if (!ok) o = make_uint4(0, 0, 0, 0);
-        // MN-major SW128: (n/64)*8192 + (k/8)*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 ; k = rb + 16 j
-        const uint32_t off = (uint32_t)(c >> 3) * 8192u + (uint32_t)(2 * j + (rb >> 3)) * 1024u +
-                             (uint32_t)(rb & 7) * 128u + (uint32_t)(((c & 7) ^ (rb & 7)) << 4);
-        *reinterpret_cast<uint4*>(a_stage + off) = o;
-      }
+    for (int j = 0; j < 2; ++j) {
+      const ZeroPairs zp = awq_zero_pairs(zq[j]);
+      uint4 o = awq_dequant_word(q[j], zp, sc[j]);
+      if (!ok) o = make_uint4(0, 0, 0, 0);
+      // MN-major SW128: (n/64)*8192 + (k/8)*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 ; k = rb + 32 j
+      const uint32_t off = (uint32_t)(c >> 3) * 8192u + (uint32_t)(4 * j + (rb >> 3)) * 1024u +
+                           (uint32_t)(rb & 7) * 128u + (uint32_t)(((c & 7) ^ (rb & 7)) << 4);
+      *reinterpret_cast<uint4*>(a_stage + off) = o;
     }
   }
 };
 
 // GEMV layout: thread dt owns k-word cw = dt % 8 (8 consecutive k) and rows n = dt/8 + 32 j, j = 0..3.
 struct GemvLayoutLoader {
+  static constexpr int kThreads = 256;
   uint32_t q[4];
   uint32_t zs[4];  // per row: fp16 scale in the low half, zero-point (0..15) in the high half
   int gidx;
@@ -172,6 +166,7 @@ struct GemvLayoutLoader {
 
 // GEMVFast layout: thread dt owns row n = dt/2 of the tile and the 32-k half h = dt%2 of the step.
 struct FastLayoutLoader {
+  static constexpr int kThreads = 256;
   uint4 q;
   uint32_t ss;  // scale (low half) | scaled zero (high half)
   int gidx;
@@ -230,14 +225,16 @@ template <> struct LoaderOf<2> { using T = FastLayoutLoader; };
 // warps: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2..5 = epilogue (TMEM lane quadrant = warp % 4),
 // 6..13 = dequant producers.  Two TMEM accumulator buffers: the epilogue of tile i overlaps the main loop
 // of tile i+1.
-constexpr int kTcThreads = 64 + 128 + kProducers;
+template <int LAYOUT>
+constexpr int tc_threads() { return 64 + 128 + LoaderOf<LAYOUT>::T::kThreads; }
 
 template <int BT, int LAYOUT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
                    const TcParams p) {
   using Cfg = TcCfg<BT>;
   constexpr int NS = Cfg::kStages;
+  constexpr int NPROD = LoaderOf<LAYOUT>::T::kThreads;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_base = smem;                                  // NS x 16 KB
@@ -257,7 +254,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmx);
     for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], kProducers / 32 + 1);  // one elected arrival per producer warp + the TMA expect_tx
+      mbar_init(&full[s], NPROD / 32 + 1);  // one elected arrival per producer warp + the TMA expect_tx
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -560,7 +557,7 @@ static cudaError_t launch_tc(const CUtensorMap& tm, const CUtensorMap& tmq, cons
   }
   const int n_work = p.n_tiles * p.m_tiles * p.ksplit;
   const int grid = n_work < sm_count() ? n_work : sm_count();
-  return launch_kernel(kern, dim3(grid), dim3(kTcThreads), Cfg::kSmemBytes, st, tm, tmq, p);
+  return launch_kernel(kern, dim3(grid), dim3(tc_threads<LAYOUT>()), Cfg::kSmemBytes, st, tm, tmq, p);
 }
 
 template <int LAYOUT>
