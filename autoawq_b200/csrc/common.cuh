@@ -65,6 +65,10 @@ __device__ __forceinline__ float ldcg_f1(const void* p) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ void sts_u4(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ----------------------------------------------------------------------- int4 -> fp16 unpack
 // (a & b) | c in one LOP3
 __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t b, uint32_t c) {
@@ -174,6 +178,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
 // L2 prefetch of a 2-D tile (no shared-memory destination, no completion tracking)
 __device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+// L2 prefetch hint for one 128-byte line (a hint: dropped, not faulted, if the address cannot be translated)
+__device__ __forceinline__ void prefetch_l2_line(const void* gsrc) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(gsrc) : "memory");
 }
 // 1-D bulk copy global -> smem (no tensor map), completion on mbarrier (bytes); size % 16 == 0
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

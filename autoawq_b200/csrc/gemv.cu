@@ -402,7 +402,8 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     gemv_v3_kernel(const __grid_constant__ CUtensorMap tmw, const __half* __restrict__ x, int64_t ldx,
                    const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                    const __half* __restrict__ bias, __half* __restrict__ y, float* __restrict__ acc_ws,
-                   int* __restrict__ tickets, int M, int K, int N, int G) {
+                   int* __restrict__ tickets, int M, int K, int N, int G, int g_shift,
+                   const uint8_t* __restrict__ next_w, long long next_bytes) {
   constexpr int SPW = V3Smem<MT>::kStagesPerWarp;
   constexpr int NS = V3Smem<MT>::kStages;
   extern __shared__ __align__(1024) uint8_t v3_smem[];
@@ -439,6 +440,14 @@ __global__ void __launch_bounds__(kV3Threads, 1)
 
   if (warp == 0) {
     // ============================================================ producer: weights never wait for PDL
+    // Lanes 8..31: pull this CTA's share of the NEXT linear's packed weights (the library learns the call
+    // sequence of a decode step) from HBM into L2, so the successor kernel starts on L2 hits and HBM never
+    // idles across the kernel boundary (per-kernel fixed cost was ~5 us of a ~13 us average launch).
+    if (lane >= kV3Warps && next_w != nullptr) {
+      const long long nline = (next_bytes + 127) / 128;
+      const long long c0 = nline * blockIdx.x / gridDim.x, c1 = nline * (blockIdx.x + 1) / gridDim.x;
+      for (long long c = c0 + (lane - kV3Warps); c < c1; c += 32 - kV3Warps) prefetch_l2_line(next_w + c * 128);
+    }
     // lane w feeds consumer warp w's private stages: no head-of-line blocking between consumers
     if (lane < kV3Warps) {
       const int w = lane;
@@ -447,18 +456,20 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       // HBM -> L2 prefetch runs kL2Ahead tiles ahead of the shared-memory ring: the ring (bounded by the
       // 227 KB of shared memory) then only has to cover L2 latency, while ~0.5 MB per SM is in flight to L2.
       constexpr int kL2Ahead = SPW + 6;
-      for (int tp = a; tp < bnd && tp < a + kL2Ahead; ++tp)
-        tma_prefetch_l2_2d(&tmw, (tp / TPC) * (kV3TileCols / 8), (tp % TPC) * kV3TileRows);
-      for (int t = a, j = 0; t < bnd; ++t, ++j) {
-        const int stage = w * SPW + (j % SPW);
-        const uint32_t ph = (uint32_t)(j / SPW) & 1u;
-        if (t + kL2Ahead < bnd) {
-          const int tp = t + kL2Ahead;
-          tma_prefetch_l2_2d(&tmw, (tp / TPC) * (kV3TileCols / 8), (tp % TPC) * kV3TileRows);
-        }
+      int cbp = a / TPC, ktp = a - cbp * TPC;      // prefetch cursor (no per-tile divisions)
+      auto pf_one = [&]() {
+        tma_prefetch_l2_2d(&tmw, cbp * (kV3TileCols / 8), ktp * kV3TileRows);
+        if (++ktp == TPC) { ktp = 0; ++cbp; }
+      };
+      for (int tp = a; tp < bnd && tp < a + kL2Ahead; ++tp) pf_one();
+      int cb = a / TPC, kt = a - cb * TPC;
+      int stage_i = 0;
+      uint32_t ph = 0;
+      for (int t = a; t < bnd; ++t) {
+        const int stage = w * SPW + stage_i;
+        if (t + kL2Ahead < bnd) pf_one();
         mbar_wait(&empty[stage], ph ^ 1);
-        const int cb = t / TPC, kt = t - cb * TPC;
-        const int grp_abs = (kt * kV3TileRows) / G;
+        const int grp_abs = (kt * kV3TileRows) >> g_shift;
         uint8_t* st = ring + (size_t)stage * kV3TileBytes;
         uint8_t* sa = aux + (size_t)stage * kV3AuxBytes;
         mbar_arrive_expect_tx(&full[stage], kV3TileBytes + kV3AuxBytes);
@@ -466,6 +477,8 @@ __global__ void __launch_bounds__(kV3Threads, 1)
         bulk_load_1d(sa, scales + (int64_t)grp_abs * N + cb * kV3TileCols, kV3ScaleBytes, &full[stage]);
         bulk_load_1d(sa + kV3ScaleBytes, qzeros + (int64_t)grp_abs * NW + cb * (kV3TileCols / 8), kV3ZeroBytes,
                      &full[stage]);
+        if (++kt == TPC) { kt = 0; ++cb; }
+        if (++stage_i == SPW) { stage_i = 0; ph ^= 1; }
       }
     }
     return;
@@ -484,12 +497,11 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   pdl_wait();  // activations, workspace, tickets, outputs belong to the stream order
 
   // activations of tile t, block b: rows 16b + {2tig, 2tig+1} and 16b + {2tig+8, 2tig+9}
-  auto load_x = [&](int t, uint32_t (&xb)[4][2]) {
+  auto load_x = [&](int t, int ktile, uint32_t (&xb)[4][2]) {
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) xb[bb][0] = xb[bb][1] = 0u;
     if (t < b_w && tok_ok) {
-      const int kt = t % TPC;
-      const __half* px = x + (int64_t)g * ldx + kt * kV3TileRows + 2 * tig;
+      const __half* px = x + (int64_t)g * ldx + ktile * kV3TileRows + 2 * tig;
 #pragma unroll
       for (int bb = 0; bb < 4; ++bb) {
         xb[bb][0] = *reinterpret_cast<const uint32_t*>(px + 16 * bb);
@@ -513,11 +525,12 @@ __global__ void __launch_bounds__(kV3Threads, 1)
 
   int cur_cb = -1, ntl = 0;
   uint32_t xcur[4][2], xnext[4][2];
-  load_x(a_w, xcur);
-  for (int t = a_w, j = 0; t < b_w; ++t, ++j) {
-    const int stage = cw * SPW + (j % SPW);
-    const uint32_t ph = (uint32_t)(j / SPW) & 1u;
-    const int cb = t / TPC, kt = t - cb * TPC;
+  int cb = a_w / TPC, kt = a_w - cb * TPC;
+  load_x(a_w, kt, xcur);
+  int stage_i = 0;
+  uint32_t ph = 0;
+  for (int t = a_w; t < b_w; ++t) {
+    const int stage = cw * SPW + stage_i;
     if (cb != cur_cb) {
       if (cur_cb >= 0 && ntl > 0) {
         // this warp's run crosses a column block: push its pending sums alone (rare)
@@ -528,7 +541,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       ntl = 0;
     }
     ++ntl;
-    load_x(t + 1, xnext);  // next tile's activations in flight while this one is computed
+    load_x(t + 1, (kt + 1 == TPC) ? 0 : kt + 1, xnext);  // next tile's activations in flight meanwhile
     mbar_wait(&full[stage], ph);
     const uint8_t* st = ring + (size_t)stage * kV3TileBytes;
     const uint8_t* sa = aux + (size_t)stage * kV3AuxBytes;
@@ -562,7 +575,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     }
 
     // ---- fold when the quantisation group (or this warp's run) ends with this tile -----------------
-    const bool group_end = (((kt + 1) * kV3TileRows) % G) == 0;
+    const bool group_end = g_shift < 31 ? ((((kt + 1) * kV3TileRows) & (G - 1)) == 0) : (kt + 1 == TPC);
     if (group_end || t + 1 == b_w) {
       // raw sums -> this warp's staging area (conflict-free float2 stores), then lane l folds word-column l
 #pragma unroll
@@ -631,6 +644,8 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       xcur[bb][0] = xnext[bb][0];
       xcur[bb][1] = xnext[bb][1];
     }
+    if (++kt == TPC) { kt = 0; ++cb; }
+    if (++stage_i == SPW) { stage_i = 0; ph ^= 1; }
   }
 
   // ---- CTA-level reduction of the per-warp column sums, grouped by column block --------------------
@@ -665,8 +680,33 @@ static int v3_sm_count() {
   return n;
 }
 
+// Successor table: decode calls the same linears in the same order every token; remember, per weight
+// tensor, which weight tensor was used next, and let the kernel prefetch it into L2 (knob 6 = 1 disables).
+struct NextW {
+  const void* ptr;
+  long long bytes;
+};
+static NextW learn_successor(const void* w, long long bytes) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, NextW> succ;
+  static const void* prev = nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (prev != nullptr && prev != w) succ[prev] = NextW{w, bytes};
+  prev = w;
+  if (succ.size() > 65536) succ.clear();
+  auto it = succ.find(w);
+  if (it == succ.end() || knob(6) != 0) return NextW{nullptr, 0};
+  return it->second;
+}
+
 template <int MT>
 static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st) {
+  const NextW nx = learn_successor(a.qweight, (long long)a.K * (a.N / 8) * 4);
+  int g_shift = 31;  // G == K: a single group
+  if ((a.G & (a.G - 1)) == 0) {
+    g_shift = 0;
+    while ((1 << g_shift) < a.G) ++g_shift;
+  }
   CUtensorMap tm;
   // qweight [K, N/8] int32 -> box {32 words = 128 B, 64 rows}, 128B swizzle
   cudaError_t e = make_tmap_2d(a.qweight, /*int32*/ 1, (uint64_t)(a.N / 8), (uint64_t)a.K, (uint64_t)(a.N / 8) * 4, 32,
@@ -686,13 +726,14 @@ static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cud
   return launch_kernel(kern, dim3(grid), dim3(kV3Threads), V3Smem<MT>::bytes, st, tm,
                        reinterpret_cast<const __half*>(a.x), a.ldx, reinterpret_cast<const __half*>(a.scales), a.qzeros,
                        reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M,
-                       a.K, a.N, a.G);
+                       a.K, a.N, a.G, g_shift, reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes);
 }
 
 // Shapes the persistent TMA-ring kernel takes: whole 64 x 256 tiles inside one quantisation group.
 bool gemv_v3_supported(const GemmArgs& a) {
+  const bool g_ok = ((a.G & (a.G - 1)) == 0) || a.G == a.K;  // power of two, or one group per column
   return gemv_gemm_layout_supported(a) && (a.N % kV3TileCols) == 0 && (a.K % kV3TileRows) == 0 &&
-         (a.G % kV3TileRows) == 0 && a.N / kV3TileCols <= 4096;
+         (a.G % kV3TileRows) == 0 && g_ok && a.N / kV3TileCols <= 4096;
 }
 
 cudaError_t gemv_v3(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st) {

@@ -333,3 +333,25 @@ def test_cuda_graph_capture(ext):
     g.replay()
     torch.cuda.synchronize()
     assert torch.allclose(y_g, m(xs), rtol=1e-3, atol=1e-3)
+
+
+def test_learned_prefetch_survives_freed_weights(ext):
+    """The M <= 8 path remembers which weight tensor followed which and prefetches the successor into L2
+    (a hint).  Freeing the successor - even returning its memory to the driver - must stay harmless."""
+    K, N, G = 1024, 512, 128
+    x = torch.randn(1, K, device=_dev(), dtype=torch.float16)
+
+    def mk(seed):
+        c = O.make_case(K, N, G, seed=seed)
+        return _t(c["qweight"]), _t(c["scales"]), _t(c["qzeros"])
+
+    a, b = mk(1), mk(2)
+    for _ in range(2):  # a -> b learned
+        ya = ext.linear_forward("gemm", x, a[0], a[1], a[2], G)
+        ext.linear_forward("gemm", x, b[0], b[1], b[2], G)
+    torch.cuda.synchronize()
+    del b
+    torch.cuda.empty_cache()  # b's pointer is now stale in the successor table
+    ya2 = ext.linear_forward("gemm", x, a[0], a[1], a[2], G)
+    torch.cuda.synchronize()
+    assert torch.equal(ya, ya2) or torch.allclose(ya.float(), ya2.float(), rtol=1e-3, atol=1e-4)
