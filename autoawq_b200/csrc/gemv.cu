@@ -440,14 +440,6 @@ __global__ void __launch_bounds__(kV3Threads, 1)
 
   if (warp == 0) {
     // ============================================================ producer: weights never wait for PDL
-    // Lanes 8..31: pull this CTA's share of the NEXT linear's packed weights (the library learns the call
-    // sequence of a decode step) from HBM into L2, so the successor kernel starts on L2 hits and HBM never
-    // idles across the kernel boundary (per-kernel fixed cost was ~5 us of a ~13 us average launch).
-    if (lane >= kV3Warps && next_w != nullptr) {
-      const long long nline = (next_bytes + 127) / 128;
-      const long long c0 = nline * blockIdx.x / gridDim.x, c1 = nline * (blockIdx.x + 1) / gridDim.x;
-      for (long long c = c0 + (lane - kV3Warps); c < c1; c += 32 - kV3Warps) prefetch_l2_line(next_w + c * 128);
-    }
     // lane w feeds consumer warp w's private stages: no head-of-line blocking between consumers
     if (lane < kV3Warps) {
       const int w = lane;
@@ -480,6 +472,15 @@ __global__ void __launch_bounds__(kV3Threads, 1)
         if (++kt == TPC) { kt = 0; ++cb; }
         if (++stage_i == SPW) { stage_i = 0; ph ^= 1; }
       }
+    }
+    __syncwarp();
+    // All of this CTA's tiles are requested: HBM would now idle while the consumers finish and the split-K
+    // epilogue runs.  Use the gap to pull this CTA's share of the NEXT linear's packed weights (the library
+    // learns the call sequence of a decode step) from HBM into L2: the successor kernel starts on L2 hits.
+    if (next_w != nullptr) {
+      const long long nline = (next_bytes + 127) / 128;
+      const long long c0 = nline * blockIdx.x / gridDim.x, c1 = nline * (blockIdx.x + 1) / gridDim.x;
+      for (long long c = c0 + lane; c < c1; c += 32) prefetch_l2_line(next_w + c * 128);
     }
     return;
   }
