@@ -238,7 +238,7 @@ def main():
     ap.add_argument("--mode", choices=["decode", "prefill"], default="decode")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--pdl", type=int, default=1, help="1: launch kernels with programmatic dependent launch")
-    ap.add_argument("--nextw", type=int, default=1, help="1: learned next-weight L2 prefetch (knob 6 = 0)")
+    ap.add_argument("--nextw", type=int, default=0, help="1: learned next-weight L2 prefetch (knob 6)")
     ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: fewer layers => INVALID as a bench value")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -299,7 +299,7 @@ def main():
     torch.cuda.set_device(dev)
     rep = Replica(dev, M, layers=a.layers, seed=rank)
     rep.ext.set_knob(4, 1 if a.pdl else 0)
-    rep.ext.set_knob(6, 0 if a.nextw else 1)
+    rep.ext.set_knob(6, 1 if a.nextw else 0)
     config["pdl"] = bool(a.pdl)
     config["next_weight_l2_prefetch"] = bool(a.nextw)
     peaks = measured_peaks()

@@ -92,8 +92,9 @@ int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200aw
  *   key 4: 1 = launch every kernel with the programmatic-dependent-launch attribute (the kernels issue
  *          their weight loads before griddepcontrol.wait, so consecutive linears overlap); default 0
  *   key 5: 1 = disable the persistent TMA-ring GEMV (use the register-staged GEMV for every M <= 8 shape)
- *   key 6: 1 = disable the learned next-weight L2 prefetch (the M <= 8 path remembers which weight tensor
- *          followed which in the call sequence and prefetches the successor's packed weights into L2)
+ *   key 6: 1 = enable the learned next-weight L2 prefetch (the M <= 8 path remembers which weight tensor
+ *          followed which in the call sequence and prefetches the successor's packed weights into L2 at the
+ *          tail of each kernel); default 0 - it measured slightly slower on B200
  */
 int b200awq_set_knob(int key, int value);
 int b200awq_get_knob(int key);

@@ -340,6 +340,7 @@ def test_learned_prefetch_survives_freed_weights(ext):
     (a hint).  Freeing the successor - even returning its memory to the driver - must stay harmless."""
     K, N, G = 1024, 512, 128
     x = torch.randn(1, K, device=_dev(), dtype=torch.float16)
+    ext.set_knob(6, 1)  # the prefetch is an opt-in experiment
 
     def mk(seed):
         c = O.make_case(K, N, G, seed=seed)
@@ -354,4 +355,5 @@ def test_learned_prefetch_survives_freed_weights(ext):
     torch.cuda.empty_cache()  # b's pointer is now stale in the successor table
     ya2 = ext.linear_forward("gemm", x, a[0], a[1], a[2], G)
     torch.cuda.synchronize()
+    ext.set_knob(6, 0)
     assert torch.equal(ya, ya2) or torch.allclose(ya.float(), ya2.float(), rtol=1e-3, atol=1e-4)
