@@ -333,11 +333,12 @@ constexpr int kV3AuxBytes = kV3ScaleBytes + kV3ZeroBytes;     // 640 B of group 
 constexpr int kV3Warps = 8;                                   // consumer warps
 constexpr int kV3Threads = 32 + kV3Warps * 32;                // producer warp + consumers
 
-template <int MT>
+template <int MT, int SPW>
 struct V3Smem {
-  // bytes in flight are what buys bandwidth (HBM latency under load is several us): as many 8 KB stages
-  // per consumer warp as the 227 KB of shared memory allow next to the per-warp reduction buffers
-  static constexpr int kStagesPerWarp = MT == 1 ? 3 : (MT <= 4 ? 2 : 1);
+  // bytes in flight are what buys bandwidth (HBM latency under load is several us): SPW 8 KB stages per
+  // consumer warp, as many as the 227 KB of shared memory allow next to the reduction buffers (and, for
+  // M <= 2, the staged activations)
+  static constexpr int kStagesPerWarp = SPW;
   static constexpr int kStages = kV3Warps * kStagesPerWarp;
   static constexpr int red_floats = kV3Warps * MT * kGvRedStride;    // per-warp raw sums [MT][288]
   static constexpr int colacc_floats = kV3Warps * MT * kV3TileCols;  // per-warp column sums [MT][256]
@@ -397,25 +398,27 @@ __device__ __forceinline__ void v3_push(float* cols, int nsrc, int src_stride, i
   }
 }
 
-template <int MT>
+template <int MT, int SPW, bool XS>
 __global__ void __launch_bounds__(kV3Threads, 1)
     gemv_v3_kernel(const __grid_constant__ CUtensorMap tmw, const __half* __restrict__ x, int64_t ldx,
                    const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                    const __half* __restrict__ bias, __half* __restrict__ y, float* __restrict__ acc_ws,
                    int* __restrict__ tickets, int M, int K, int N, int G, int g_shift,
                    const uint8_t* __restrict__ next_w, long long next_bytes) {
-  constexpr int SPW = V3Smem<MT>::kStagesPerWarp;
-  constexpr int NS = V3Smem<MT>::kStages;
+  constexpr int NS = V3Smem<MT, SPW>::kStages;
   extern __shared__ __align__(1024) uint8_t v3_smem[];
   uint8_t* ring = v3_smem;                                   // NS x 8 KB weight tiles (1 KB aligned: swizzle atoms)
   uint8_t* aux = v3_smem + (size_t)NS * kV3TileBytes;        // NS x (256 scales + 32 zero words)
   float* red = reinterpret_cast<float*>(aux + (size_t)NS * kV3AuxBytes);
-  float* colacc = red + V3Smem<MT>::red_floats;
-  uint64_t* full = reinterpret_cast<uint64_t*>(colacc + V3Smem<MT>::colacc_floats);
+  float* colacc = red + V3Smem<MT, SPW>::red_floats;
+  uint64_t* full = reinterpret_cast<uint64_t*>(colacc + V3Smem<MT, SPW>::colacc_floats);
   uint64_t* empty = full + NS;
   int* flags = reinterpret_cast<int*>(empty + NS);   // [0..7] per-warp push flags, [8] CTA flag,
   int* warp_cb = flags + 16;                         // [8] column block of each warp's pending sums
   int* warp_ntl = warp_cb + 8;                       // [8] tiles those sums cover
+  // XS: the activations of all MT tokens staged once per CTA (row stride K + 8 halves)
+  __half* xs = reinterpret_cast<__half*>(v3_smem + V3Smem<MT, SPW>::bytes);
+  const int xs_stride = K + 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NW = N >> 3;
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     }
     fence_mbar_init();
   }
-  for (int i = tid; i < V3Smem<MT>::colacc_floats; i += kV3Threads) colacc[i] = 0.f;
+  for (int i = tid; i < V3Smem<MT, SPW>::colacc_floats; i += kV3Threads) colacc[i] = 0.f;
   __syncthreads();
 
   if (warp == 0) {
@@ -502,14 +505,35 @@ __global__ void __launch_bounds__(kV3Threads, 1)
 #pragma unroll
     for (int bb = 0; bb < 4; ++bb) xb[bb][0] = xb[bb][1] = 0u;
     if (t < b_w && tok_ok) {
-      const __half* px = x + (int64_t)g * ldx + ktile * kV3TileRows + 2 * tig;
+      if (XS) {
+        const __half* px = xs + g * xs_stride + ktile * kV3TileRows + 2 * tig;
 #pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
-        xb[bb][0] = *reinterpret_cast<const uint32_t*>(px + 16 * bb);
-        xb[bb][1] = *reinterpret_cast<const uint32_t*>(px + 16 * bb + 8);
+        for (int bb = 0; bb < 4; ++bb) {
+          xb[bb][0] = *reinterpret_cast<const uint32_t*>(px + 16 * bb);
+          xb[bb][1] = *reinterpret_cast<const uint32_t*>(px + 16 * bb + 8);
+        }
+      } else {
+        const __half* px = x + (int64_t)g * ldx + ktile * kV3TileRows + 2 * tig;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          xb[bb][0] = *reinterpret_cast<const uint32_t*>(px + 16 * bb);
+          xb[bb][1] = *reinterpret_cast<const uint32_t*>(px + 16 * bb + 8);
+        }
       }
     }
   };
+  if (XS) {
+    // stage x[m][0..K) for the real tokens (16-byte chunks; K % 64 == 0, rows 8-byte aligned at least)
+    const int chunks = K / 8;
+    for (int i = ct; i < M * chunks; i += kV3Warps * 32) {
+      const int m = i / chunks, c8 = (i - m * chunks) * 8;
+      const __half* src = x + (int64_t)m * ldx + c8;
+      uint2 lo = *reinterpret_cast<const uint2*>(src), hi = *reinterpret_cast<const uint2*>(src + 4);
+      *reinterpret_cast<uint2*>(xs + m * xs_stride + c8) = lo;
+      *reinterpret_cast<uint2*>(xs + m * xs_stride + c8 + 4) = hi;
+    }
+    named_bar_sync_gv(1, kV3Warps * 32);
+  }
 
   float acc[4][4][4];
   float xs_acc[4];
@@ -702,7 +726,7 @@ static NextW learn_successor(const void* w, long long bytes) {
   return it->second;
 }
 
-template <int MT>
+template <int MT, int SPW, bool XS>
 static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st) {
   const NextW nx = learn_successor(a.qweight, (long long)a.K * (a.N / 8) * 4);
   int g_shift = 31;  // G == K: a single group
@@ -715,21 +739,16 @@ static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cud
   cudaError_t e = make_tmap_2d(a.qweight, /*int32*/ 1, (uint64_t)(a.N / 8), (uint64_t)a.K, (uint64_t)(a.N / 8) * 4, 32,
                                kV3TileRows, &tm);
   if (e != cudaSuccess) return e;
-  auto kern = gemv_v3_kernel<MT>;
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V3Smem<MT>::bytes);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
+  auto kern = gemv_v3_kernel<MT, SPW, XS>;
+  const size_t smem = V3Smem<MT, SPW>::bytes + (XS ? (size_t)MT * (a.K + 8) * 2 : 0);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   const int T = (a.N / kV3TileCols) * (a.K / kV3TileRows);
   const int grid = T < v3_sm_count() ? T : v3_sm_count();
-  return launch_kernel(kern, dim3(grid), dim3(kV3Threads), V3Smem<MT>::bytes, st, tm,
-                       reinterpret_cast<const __half*>(a.x), a.ldx, reinterpret_cast<const __half*>(a.scales), a.qzeros,
-                       reinterpret_cast<const __half*>(a.bias), reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M,
-                       a.K, a.N, a.G, g_shift, reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes);
+  return launch_kernel(kern, dim3(grid), dim3(kV3Threads), smem, st, tm, reinterpret_cast<const __half*>(a.x), a.ldx,
+                       reinterpret_cast<const __half*>(a.scales), a.qzeros, reinterpret_cast<const __half*>(a.bias),
+                       reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M, a.K, a.N, a.G, g_shift,
+                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes);
 }
 
 // Shapes the persistent TMA-ring kernel takes: whole 64 x 256 tiles inside one quantisation group.
@@ -740,10 +759,18 @@ bool gemv_v3_supported(const GemmArgs& a) {
 }
 
 cudaError_t gemv_v3(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st) {
-  if (a.M <= 1) return launch_v3<1>(a, acc_ws, tickets, st);
-  if (a.M <= 2) return launch_v3<2>(a, acc_ws, tickets, st);
-  if (a.M <= 4) return launch_v3<4>(a, acc_ws, tickets, st);
-  return launch_v3<8>(a, acc_ws, tickets, st);
+  constexpr size_t kMaxSmem = 227 * 1024;
+  if (a.M <= 1) {
+    // staged activations (no global loads in the consumer loop) + 2 stages per warp, if K fits
+    if (knob(7) == 0 && V3Smem<1, 2>::bytes + (size_t)(a.K + 8) * 2 <= kMaxSmem) return launch_v3<1, 2, true>(a, acc_ws, tickets, st);
+    return launch_v3<1, 3, false>(a, acc_ws, tickets, st);
+  }
+  if (a.M <= 2) {
+    if (knob(7) == 0 && V3Smem<2, 2>::bytes + (size_t)2 * (a.K + 8) * 2 <= kMaxSmem) return launch_v3<2, 2, true>(a, acc_ws, tickets, st);
+    return launch_v3<2, 2, false>(a, acc_ws, tickets, st);
+  }
+  if (a.M <= 4) return launch_v3<4, 2, false>(a, acc_ws, tickets, st);
+  return launch_v3<8, 1, false>(a, acc_ws, tickets, st);
 }
 
 }  // namespace b200awq
