@@ -95,6 +95,7 @@ int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200aw
  *   key 6: 1 = enable the learned next-weight L2 prefetch (the M <= 8 path remembers which weight tensor
  *          followed which in the call sequence and prefetches the successor's packed weights into L2 at the
  *          tail of each kernel); default 0 - it measured slightly slower on B200
+ *   key 7: 1 = stage the activations in shared memory in the persistent GEMV (M <= 2); default 0
  */
 int b200awq_set_knob(int key, int value);
 int b200awq_get_knob(int key);

@@ -13,6 +13,21 @@ from autoawq_b200 import ext  # noqa: E402
 
 dev = torch.device("cuda:0")
 what = sys.argv[1] if len(sys.argv) > 1 else "gemv"
+if what == "layer":
+    # one Llama-3-8B layer's four linears at M = 1, weights rotated through a pool > L2: the launch mix bench.py times
+    G = 128
+    shapes = [(4096, 6144), (4096, 4096), (4096, 28672), (14336, 4096)]
+    pool = []
+    for rep in range(3):
+        for (K, N) in shapes:
+            pool.append((torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, device=dev),
+                         (torch.rand((K // G, N), device=dev) * 0.01 + 0.001).half(),
+                         torch.randint(-2**31, 2**31 - 1, (K // G, N // 8), dtype=torch.int32, device=dev),
+                         torch.randn((1, K), device=dev, dtype=torch.float16)))
+    for qw, sc, qz, x in pool:
+        ext.linear_forward("gemm", x, qw, sc, qz, G)
+    torch.cuda.synchronize()
+    sys.exit(0)
 K, N, M = {"gemv": (4096, 4096, 1), "gemv_big": (4096, 28672, 1), "gemm": (4096, 4096, 4096),
            "gemm64": (4096, 14336, 64)}[what]
 G = 128
