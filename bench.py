@@ -325,7 +325,10 @@ def main():
     if a.mode == "decode":
         ach = alg_bytes / n_lin / avg_launch_s / 1e9
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
+                "frac": round(ach / peaks["hbm_gbs"], 4),
+                # dram__bytes_read + write per launch, averaged over one layer's four GEMV launches, from the committed
+                # ncu --set full capture profiles/r01_gemv_v3_one_layer_M1.md (113.69 MB / 4; algorithmic 113.31 MB / 4)
+                "traffic": 28422000 if a.layers == LAYERS else None,
                 "kernel": "gemv_v3_kernel<1> (persistent TMA-ring GEMV)", "peak_src": peaks["src"] + " (hbm_gbs)",
                 "per_launch": {"avg_us": round(avg_launch_s * 1e6, 2), "alg_bytes": alg_bytes // n_lin,
                                "launches_timed": n_lin * a.steps,
