@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200awq_silu_and_mul": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p]),
     "b200awq_set_knob": (_c_int, [_c_int, _c_int]),
     "b200awq_get_knob": (_c_int, [_c_int]),
+    "b200awq_debug_read": (_c_int, [_c_void_p, _c_size_t]),
 }
 
 

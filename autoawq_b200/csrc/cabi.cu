@@ -79,6 +79,8 @@ int b200awq_set_knob(int key, int value) {
 }
 int b200awq_get_knob(int key) { return knob(key); }
 
+int b200awq_debug_read(void* host_dst, size_t bytes) { return fold(gemv_v3_debug_read(host_dst, bytes)); }
+
 int b200awq_dequantize_gemm(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out_f16, int K,
                             int N, int group_size, b200awq_stream_t stream) {
   const int G = group_size <= 0 ? K : group_size;

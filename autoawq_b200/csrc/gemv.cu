@@ -324,6 +324,18 @@ cudaError_t gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cud
 //     column block is known without any host-side schedule.
 namespace b200awq {
 
+// Phase timestamps (globaltimer, ns) of the last persistent-GEMV launch, one row of 8 per CTA; written only when
+// knob 3 is set.  Read back with b200awq_debug_read().
+__device__ unsigned long long g_v3_dbg[256 * 8];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+cudaError_t gemv_v3_debug_read(void* dst, size_t bytes) {
+  return cudaMemcpyFromSymbol(dst, g_v3_dbg, bytes < sizeof(g_v3_dbg) ? bytes : sizeof(g_v3_dbg));
+}
+
 constexpr int kV3TileRows = 64;
 constexpr int kV3TileCols = 256;
 constexpr int kV3TileBytes = kV3TileRows * 128;               // 8 KB of packed weights
@@ -404,7 +416,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
                    const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                    const __half* __restrict__ bias, __half* __restrict__ y, float* __restrict__ acc_ws,
                    int* __restrict__ tickets, int M, int K, int N, int G, int g_shift,
-                   const uint8_t* __restrict__ next_w, long long next_bytes) {
+                   const uint8_t* __restrict__ next_w, long long next_bytes, int dbg) {
   constexpr int NS = V3Smem<MT, SPW>::kStages;
   extern __shared__ __align__(1024) uint8_t v3_smem[];
   uint8_t* ring = v3_smem;                                   // NS x 8 KB weight tiles (1 KB aligned: swizzle atoms)
@@ -429,6 +441,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   const int ntile = t1 - t0;
 
   pdl_trigger();
+  if (dbg && tid == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 0] = gtimer();
   if (tid == 0) {
     if ((smem_u32(v3_smem) & 1023u) != 0) __trap();  // the 128B-swizzle read pattern assumes 1 KB aligned stages
     tma_prefetch_desc(&tmw);
@@ -499,6 +512,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   const int b_w = t0 + (int)((int64_t)ntile * (cw + 1) / kV3Warps);
 
   pdl_wait();  // activations, workspace, tickets, outputs belong to the stream order
+  if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 1] = gtimer();
 
   // activations of tile t, block b: rows 16b + {2tig, 2tig+1} and 16b + {2tig+8, 2tig+9}
   auto load_x = [&](int t, int ktile, uint32_t (&xb)[4][2]) {
@@ -568,6 +582,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     ++ntl;
     load_x(t + 1, (kt + 1 == TPC) ? 0 : kt + 1, xnext);  // next tile's activations in flight meanwhile
     mbar_wait(&full[stage], ph);
+    if (dbg && ct == 0 && t == a_w && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 2] = gtimer();
     const uint8_t* st = ring + (size_t)stage * kV3TileBytes;
     const uint8_t* sa = aux + (size_t)stage * kV3AuxBytes;
 
@@ -674,11 +689,13 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   }
 
   // ---- CTA-level reduction of the per-warp column sums, grouped by column block --------------------
+  if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 3] = gtimer();
   if (lane == 0) {
     warp_cb[cw] = (ntl > 0) ? cur_cb : -1;
     warp_ntl[cw] = ntl;
   }
   named_bar_sync_gv(1, kV3Warps * 32);
+  if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 4] = gtimer();
   int w0 = 0;
   while (w0 < kV3Warps) {
     const int cb = warp_cb[w0];
@@ -692,6 +709,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
                                  &flags[8], bias, y, acc_ws, tickets, M, N);
     w0 = w1;
   }
+  if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 5] = gtimer();
 }
 
 static int v3_sm_count() {
@@ -748,7 +766,7 @@ static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cud
   return launch_kernel(kern, dim3(grid), dim3(kV3Threads), smem, st, tm, reinterpret_cast<const __half*>(a.x), a.ldx,
                        reinterpret_cast<const __half*>(a.scales), a.qzeros, reinterpret_cast<const __half*>(a.bias),
                        reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M, a.K, a.N, a.G, g_shift,
-                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes);
+                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3));
 }
 
 // Shapes the persistent TMA-ring kernel takes: whole 64 x 256 tiles inside one quantisation group.

@@ -66,6 +66,7 @@ cudaError_t make_tmap_2d(const void* ptr, int elem_kind, uint64_t inner, uint64_
 bool gemv_gemm_layout_supported(const GemmArgs& a);
 bool gemv_v3_supported(const GemmArgs& a);
 cudaError_t gemv_v3(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st);
+cudaError_t gemv_v3_debug_read(void* dst, size_t bytes);
 cudaError_t gemv_gemm_layout(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t st);
 cudaError_t gemv_gemv_layout(const GemmArgs& a, cudaStream_t st);
 cudaError_t gemv_fast_layout(const FastArgs& a, cudaStream_t st);

@@ -88,7 +88,7 @@ int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200aw
  *   key 0: GEMV rows per warp override: 32 / 64 / 128 (0 = heuristic)
  *   key 1: tensor-core path split-K override (0 = heuristic)
  *   key 2: M threshold at or below which the CUDA-core GEMV is used (default 8)
- *   key 3: reserved
+ *   key 3: 1 = the persistent GEMV records per-CTA phase timestamps (read with b200awq_debug_read)
  *   key 4: 1 = launch every kernel with the programmatic-dependent-launch attribute (the kernels issue
  *          their weight loads before griddepcontrol.wait, so consecutive linears overlap); default 0
  *   key 5: 1 = disable the persistent TMA-ring GEMV (use the register-staged GEMV for every M <= 8 shape)
@@ -99,6 +99,10 @@ int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200aw
  */
 int b200awq_set_knob(int key, int value);
 int b200awq_get_knob(int key);
+/* Copies the phase timestamps of the last persistent-GEMV launch (knob 3) to HOST memory: per CTA 8 x uint64 ns
+ * (globaltimer): [0] kernel entry, [1] after the PDL wait, [2] first tile landed, [3] consumer warp 0 done,
+ * [4] all consumer warps done, [5] split-K push / finalisation done.  Synchronises the device. */
+int b200awq_debug_read(void* host_dst, size_t bytes);
 
 #ifdef __cplusplus
 }
