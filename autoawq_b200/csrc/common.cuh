@@ -56,6 +56,25 @@ __device__ __forceinline__ float ldcg_f1(const void* p) {
   return r;
 }
 
+// Split-K hand-off without sequentially-consistent fences (__threadfence() = fence.sc.gpu = MEMBAR.SC.GPU +
+// L1 invalidate, measured at microseconds in the GEMV tail): contributors add with relaxed REDs, synchronise
+// on a CTA barrier, ONE thread bumps the ticket with acq_rel at gpu scope (release is cumulative over what the
+// barrier ordered before it); the thread that sees the final count acquires, and the barrier after it orders
+// the rest of the CTA.
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ int atom_add_acq_rel(int* p, int v) {
+  int old;
+  asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ float ld_relaxed_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
 // attribute may start while its predecessor is still running.  pdl_trigger() lets OUR successor start
 // early; pdl_wait() blocks until the predecessor grid has completed and its writes are visible - it must

@@ -359,16 +359,11 @@ struct V3Smem {
 };
 
 // Shared by the warp-level (NT = 32) and CTA-level (NT = 256) pushes: add `cols` [MT][256] (shared memory,
-// summed over `nsrc` sources `src_stride` floats apart) into the fp32 workspace, count `ntl` tiles on the
-// column block's ticket and, if this was the last contribution, round to fp16 (+ bias) and re-zero.
+// summed over `nsrc` sources `src_stride` floats apart) into the fp32 workspace (relaxed REDs).
 template <int MT, int NT>
-__device__ __forceinline__ void v3_push(float* cols, int nsrc, int src_stride, int cb, int ntl, int TPC, int t,
-                                        int* flag, const __half* __restrict__ bias, __half* __restrict__ y,
-                                        float* __restrict__ acc_ws, int* __restrict__ tickets, int M, int N) {
+__device__ __forceinline__ void v3_add_cols(float* cols, int nsrc, int src_stride, int cb, int t,
+                                            float* __restrict__ acc_ws, int M, int N) {
   const int n_base = cb * kV3TileCols;
-  auto sync = [&]() {
-    if (NT == 32) __syncwarp(); else named_bar_sync_gv(1, NT);
-  };
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
     if (m < M) {
@@ -378,36 +373,42 @@ __device__ __forceinline__ void v3_push(float* cols, int nsrc, int src_stride, i
           v += cols[sidx * src_stride + m * kV3TileCols + c];
           cols[sidx * src_stride + m * kV3TileCols + c] = 0.f;
         }
-        atomicAdd(&acc_ws[(int64_t)m * N + n_base + c], v);
+        red_add_f32(&acc_ws[(int64_t)m * N + n_base + c], v);
       }
     }
   }
-  __threadfence();
-  sync();
-  if (t == 0) {
-    const int prev = atomicAdd(&tickets[cb], ntl);
-    *flag = (prev + ntl == TPC);
-  }
-  sync();
-  const bool last = *flag != 0;
-  sync();  // the flag may be rewritten by a later push
-  if (last) {
-    __threadfence();
+}
+// The last contributor of column block `cb` rounds to fp16 (+ bias) and restores the zeros.
+template <int MT, int NT>
+__device__ __forceinline__ void v3_finalize(int cb, int t, const __half* __restrict__ bias, __half* __restrict__ y,
+                                            float* __restrict__ acc_ws, int* __restrict__ tickets, int M, int N) {
+  const int n_base = cb * kV3TileCols;
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      if (m < M) {
-        for (int c = t; c < kV3TileCols; c += NT) {
-          const int n = n_base + c;
-          float* p = &acc_ws[(int64_t)m * N + n];
-          float v = ldcg_f1(p);
-          *p = 0.f;
-          if (bias != nullptr) v += __half2float(bias[n]);
-          y[(int64_t)m * N + n] = __float2half_rn(v);
-        }
+  for (int m = 0; m < MT; ++m) {
+    if (m < M) {
+      for (int c = t; c < kV3TileCols; c += NT) {
+        const int n = n_base + c;
+        float* p = &acc_ws[(int64_t)m * N + n];
+        float v = ld_relaxed_f32(p);
+        *p = 0.f;
+        if (bias != nullptr) v += __half2float(bias[n]);
+        y[(int64_t)m * N + n] = __float2half_rn(v);
       }
     }
-    if (t == 0) tickets[cb] = 0;
   }
+  if (t == 0) tickets[cb] = 0;
+}
+// Warp-level push (a warp's run crossed a column block; rare).
+template <int MT>
+__device__ __forceinline__ void v3_push_warp(float* cols, int cb, int ntl, int TPC, int lane,
+                                             const __half* __restrict__ bias, __half* __restrict__ y,
+                                             float* __restrict__ acc_ws, int* __restrict__ tickets, int M, int N) {
+  v3_add_cols<MT, 32>(cols, 1, 0, cb, lane, acc_ws, M, N);
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) last = (atom_add_acq_rel(&tickets[cb], ntl) + ntl == TPC);
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) v3_finalize<MT, 32>(cb, lane, bias, y, acc_ws, tickets, M, N);
 }
 
 template <int MT, int SPW, bool XS>
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       if (cur_cb >= 0 && ntl > 0) {
         // this warp's run crosses a column block: push its pending sums alone (rare)
         __syncwarp();
-        v3_push<MT, 32>(my_col, 1, 0, cur_cb, ntl, TPC, lane, &flags[cw], bias, y, acc_ws, tickets, M, N);
+        v3_push_warp<MT>(my_col, cur_cb, ntl, TPC, lane, bias, y, acc_ws, tickets, M, N);
       }
       cur_cb = cb;
       ntl = 0;
@@ -696,19 +697,37 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   }
   named_bar_sync_gv(1, kV3Warps * 32);
   if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 4] = gtimer();
-  int w0 = 0;
-  while (w0 < kV3Warps) {
-    const int cb = warp_cb[w0];
-    int w1 = w0 + 1, tiles = warp_ntl[w0];
-    while (w1 < kV3Warps && warp_cb[w1] == cb) {
-      tiles += warp_ntl[w1];
-      ++w1;
+  // pass 1: all column-block groups of this CTA (consecutive warps with the same block) -> workspace
+  {
+    int w0 = 0;
+    while (w0 < kV3Warps) {
+      const int cbg = warp_cb[w0];
+      int w1 = w0 + 1;
+      while (w1 < kV3Warps && warp_cb[w1] == cbg) ++w1;
+      if (cbg >= 0)
+        v3_add_cols<MT, kV3Warps * 32>(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cbg, ct, acc_ws,
+                                       M, N);
+      w0 = w1;
     }
-    if (cb >= 0)
-      v3_push<MT, kV3Warps * 32>(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cb, tiles, TPC, ct,
-                                 &flags[8], bias, y, acc_ws, tickets, M, N);
-    w0 = w1;
   }
+  named_bar_sync_gv(1, kV3Warps * 32);
+  // pass 2: thread w bumps the ticket of the group that STARTS at warp w (tickets in parallel, one round trip)
+  if (ct < kV3Warps) {
+    const int w = ct;
+    const int cbg = warp_cb[w];
+    int is_last = 0;
+    if (cbg >= 0 && (w == 0 || warp_cb[w - 1] != cbg)) {
+      int tiles = 0;
+      for (int w1 = w; w1 < kV3Warps && warp_cb[w1] == cbg; ++w1) tiles += warp_ntl[w1];
+      is_last = (atom_add_acq_rel(&tickets[cbg], tiles) + tiles == TPC);
+    }
+    flags[w] = is_last;
+  }
+  named_bar_sync_gv(1, kV3Warps * 32);
+  // pass 3: finalise the blocks for which this CTA was the last contributor
+#pragma unroll 1
+  for (int w = 0; w < kV3Warps; ++w)
+    if (flags[w]) v3_finalize<MT, kV3Warps * 32>(warp_cb[w], ct, bias, y, acc_ws, tickets, M, N);
   if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 5] = gtimer();
 }
 
