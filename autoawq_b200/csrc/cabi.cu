@@ -9,8 +9,8 @@
 
 namespace b200awq {
 
-static std::atomic<int> g_knobs[8] = {{0}, {0}, {8}, {0}, {0}, {0}, {0}, {0}};
-int knob(int key) { return (key >= 0 && key < 8) ? g_knobs[key].load(std::memory_order_relaxed) : 0; }
+static std::atomic<int> g_knobs[16] = {{0}, {0}, {8}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}};
+int knob(int key) { return (key >= 0 && key < 16) ? g_knobs[key].load(std::memory_order_relaxed) : 0; }
 
 static thread_local char g_cuda_err[256] = "";
 
@@ -73,7 +73,7 @@ size_t b200awq_workspace_bytes(int M, int K, int N) {
 }
 
 int b200awq_set_knob(int key, int value) {
-  if (key < 0 || key >= 8) return B200AWQ_EINVAL;
+  if (key < 0 || key >= 16) return B200AWQ_EINVAL;
   g_knobs[key].store(value, std::memory_order_relaxed);
   return B200AWQ_OK;
 }

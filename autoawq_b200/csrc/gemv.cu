@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
                    const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                    const __half* __restrict__ bias, __half* __restrict__ y, float* __restrict__ acc_ws,
                    int* __restrict__ tickets, int M, int K, int N, int G, int g_shift,
-                   const uint8_t* __restrict__ next_w, long long next_bytes, int dbg) {
+                   const uint8_t* __restrict__ next_w, long long next_bytes, int dbg, int l2_ahead) {
   constexpr int NS = V3Smem<MT, SPW>::kStages;
   extern __shared__ __align__(1024) uint8_t v3_smem[];
   uint8_t* ring = v3_smem;                                   // NS x 8 KB weight tiles (1 KB aligned: swizzle atoms)
@@ -464,19 +464,20 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       const int bnd = t0 + (int)((int64_t)ntile * (w + 1) / kV3Warps);
       // HBM -> L2 prefetch runs kL2Ahead tiles ahead of the shared-memory ring: the ring (bounded by the
       // 227 KB of shared memory) then only has to cover L2 latency, while ~0.5 MB per SM is in flight to L2.
-      constexpr int kL2Ahead = SPW + 6;
+      const int kL2Ahead = l2_ahead > 0 ? SPW + l2_ahead : 0;  // 0: no L2 prefetch
       int cbp = a / TPC, ktp = a - cbp * TPC;      // prefetch cursor (no per-tile divisions)
       auto pf_one = [&]() {
         tma_prefetch_l2_2d(&tmw, cbp * (kV3TileCols / 8), ktp * kV3TileRows);
         if (++ktp == TPC) { ktp = 0; ++cbp; }
       };
       for (int tp = a; tp < bnd && tp < a + kL2Ahead; ++tp) pf_one();
+      const bool do_pf = kL2Ahead > 0;
       int cb = a / TPC, kt = a - cb * TPC;
       int stage_i = 0;
       uint32_t ph = 0;
       for (int t = a; t < bnd; ++t) {
         const int stage = w * SPW + stage_i;
-        if (t + kL2Ahead < bnd) pf_one();
+        if (do_pf && t + kL2Ahead < bnd) pf_one();
         mbar_wait(&empty[stage], ph ^ 1);
         const int grp_abs = (kt * kV3TileRows) >> g_shift;
         uint8_t* st = ring + (size_t)stage * kV3TileBytes;
@@ -711,6 +712,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     }
   }
   named_bar_sync_gv(1, kV3Warps * 32);
+  if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 5] = gtimer();
   // pass 2: thread w bumps the ticket of the group that STARTS at warp w (tickets in parallel, one round trip)
   if (ct < kV3Warps) {
     const int w = ct;
@@ -724,11 +726,12 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     flags[w] = is_last;
   }
   named_bar_sync_gv(1, kV3Warps * 32);
+  if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 6] = gtimer();
   // pass 3: finalise the blocks for which this CTA was the last contributor
 #pragma unroll 1
   for (int w = 0; w < kV3Warps; ++w)
     if (flags[w]) v3_finalize<MT, kV3Warps * 32>(warp_cb[w], ct, bias, y, acc_ws, tickets, M, N);
-  if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 5] = gtimer();
+  if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 7] = gtimer();
 }
 
 static int v3_sm_count() {
@@ -785,7 +788,7 @@ static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cud
   return launch_kernel(kern, dim3(grid), dim3(kV3Threads), smem, st, tm, reinterpret_cast<const __half*>(a.x), a.ldx,
                        reinterpret_cast<const __half*>(a.scales), a.qzeros, reinterpret_cast<const __half*>(a.bias),
                        reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M, a.K, a.N, a.G, g_shift,
-                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3));
+                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3), knob(8) > 0 ? knob(8) - 1 : 6);
 }
 
 // Shapes the persistent TMA-ring kernel takes: whole 64 x 256 tiles inside one quantisation group.
@@ -801,6 +804,8 @@ cudaError_t gemv_v3(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t
     // knob 7 = 1: stage the activations in shared memory (2 ring stages per warp instead of 3).  Measured r1:
     // 477 vs 498 tok/s - the x loads were not the stall, the third stage is worth more.
     if (knob(7) != 0 && V3Smem<1, 2>::bytes + (size_t)(a.K + 8) * 2 <= kMaxSmem) return launch_v3<1, 2, true>(a, acc_ws, tickets, st);
+    if (knob(9) == 1) return launch_v3<1, 1, false>(a, acc_ws, tickets, st);
+    if (knob(9) == 2) return launch_v3<1, 2, false>(a, acc_ws, tickets, st);
     return launch_v3<1, 3, false>(a, acc_ws, tickets, st);
   }
   if (a.M <= 2) {

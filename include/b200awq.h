@@ -96,12 +96,15 @@ int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200aw
  *          followed which in the call sequence and prefetches the successor's packed weights into L2 at the
  *          tail of each kernel); default 0 - it measured slightly slower on B200
  *   key 7: 1 = stage the activations in shared memory in the persistent GEMV (M <= 2); default 0
+ *   key 8: persistent GEMV L2-prefetch distance + 1 in tiles (1 = off; 0 = default 6)
+ *   key 9: persistent GEMV ring stages per consumer warp for M = 1 (1 / 2; 0 = default 3)
  */
 int b200awq_set_knob(int key, int value);
 int b200awq_get_knob(int key);
 /* Copies the phase timestamps of the last persistent-GEMV launch (knob 3) to HOST memory: per CTA 8 x uint64 ns
  * (globaltimer): [0] kernel entry, [1] after the PDL wait, [2] first tile landed, [3] consumer warp 0 done,
- * [4] all consumer warps done, [5] split-K push / finalisation done.  Synchronises the device. */
+ * [4] all consumer warps done, [5] partial sums added (REDs issued), [6] tickets bumped, [7] finalisation done.
+ * Synchronises the device. */
 int b200awq_debug_read(void* host_dst, size_t bytes);
 
 #ifdef __cplusplus

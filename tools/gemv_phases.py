@@ -30,7 +30,8 @@ for (K, N) in [(4096, 4096), (4096, 6144), (4096, 28672), (14336, 4096)]:
     ext.set_knob(3, 0)
     a = np.stack(rows)  # [iters, 148, 8]
     t0 = a[:, :, 0].min(axis=1, keepdims=True)  # earliest CTA entry of the launch
-    names = ["entry(skew)", "pdl_wait done", "first tile landed", "warp0 loop done", "all warps done", "push done"]
+    names = ["entry(skew)", "pdl_wait done", "first tile landed", "warp0 loop done", "all warps done",
+             "REDs issued+barrier", "tickets+barrier", "finalise done"]
     print(f"K={K} N={N}: ns since the first CTA entered (median over CTAs, max over CTAs), median over {a.shape[0]} launches")
     for i, nm in enumerate(names):
         d = a[:, :, i] - t0
