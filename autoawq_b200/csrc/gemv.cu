@@ -462,8 +462,9 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       const int w = lane;
       const int a = t0 + (int)((int64_t)ntile * w / kV3Warps);
       const int bnd = t0 + (int)((int64_t)ntile * (w + 1) / kV3Warps);
-      // HBM -> L2 prefetch runs kL2Ahead tiles ahead of the shared-memory ring: the ring (bounded by the
-      // 227 KB of shared memory) then only has to cover L2 latency, while ~0.5 MB per SM is in flight to L2.
+      // Optional HBM -> L2 prefetch kL2Ahead tiles ahead of the shared-memory ring (knob 8).  Measured r1 (ring
+      // sweep in profiles/): no gain - 19.5 us without vs 20.7 us with it on 4096x28672 - the 24-stage ring already
+      // saturates what the consumers can drain, extra requests only lengthen the queues.  Default: off.
       const int kL2Ahead = l2_ahead > 0 ? SPW + l2_ahead : 0;  // 0: no L2 prefetch
       int cbp = a / TPC, ktp = a - cbp * TPC;      // prefetch cursor (no per-tile divisions)
       auto pf_one = [&]() {
@@ -788,7 +789,7 @@ static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cud
   return launch_kernel(kern, dim3(grid), dim3(kV3Threads), smem, st, tm, reinterpret_cast<const __half*>(a.x), a.ldx,
                        reinterpret_cast<const __half*>(a.scales), a.qzeros, reinterpret_cast<const __half*>(a.bias),
                        reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M, a.K, a.N, a.G, g_shift,
-                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3), knob(8) > 0 ? knob(8) - 1 : 6);
+                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3), knob(8) > 0 ? knob(8) - 1 : 0);
 }
 
 // Shapes the persistent TMA-ring kernel takes: whole 64 x 256 tiles inside one quantisation group.

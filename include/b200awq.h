@@ -96,7 +96,7 @@ int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200aw
  *          followed which in the call sequence and prefetches the successor's packed weights into L2 at the
  *          tail of each kernel); default 0 - it measured slightly slower on B200
  *   key 7: 1 = stage the activations in shared memory in the persistent GEMV (M <= 2); default 0
- *   key 8: persistent GEMV L2-prefetch distance + 1 in tiles (1 = off; 0 = default 6)
+ *   key 8: persistent GEMV L2-prefetch distance + 1 in tiles (0 / 1 = off, the default)
  *   key 9: persistent GEMV ring stages per consumer warp for M = 1 (1 / 2; 0 = default 3)
  */
 int b200awq_set_knob(int key, int value);
