@@ -74,25 +74,30 @@ struct GemmLayoutLoader {
   int gidx[2];
   __device__ __forceinline__ void init() { gidx[0] = gidx[1] = -1; zq[0] = zq[1] = 0; sc[0] = sc[1] = make_uint4(0, 0, 0, 0); }
   __device__ __forceinline__ void load(const TcParams& p, int nt, int k0, int dt) {
-    const int NW = p.N >> 3;
-    const int c = dt & 15, rb = dt >> 4;
-    const int wc = nt * 16 + c;
+    // 32-bit word offsets (K * N/8 < 2^32 for every real shape) keep the address arithmetic to a few
+    // instructions per load; the first version spent ~90 instructions per k-step on 64-bit multiplies.
+    const uint32_t NW = (uint32_t)p.N >> 3;
+    const uint32_t c = dt & 15, rb = dt >> 4;
+    const uint32_t wc = (uint32_t)nt * 16 + c;
     const bool ok = wc < NW;
-    const int32_t* src = p.qweight + (int64_t)(k0 + rb) * NW + wc;
+    const uint32_t row0 = ((uint32_t)k0 + rb) * NW + wc;
+    const uint32_t row16 = 16u * NW;
+    const int32_t* src = p.qweight + row0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       q[j] = 0u;
-      if (ok) q[j] = ldg_stream_u1(src + (int64_t)(16 * j) * NW);
+      if (ok) q[j] = ldg_stream_u1(src + j * row16);
     }
     // rows j = 0,1 (< 32) and j = 2,3 (>= 32) may sit in different groups when G == 32
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int g = (k0 + rb + 32 * h) >> p.g_shift;   // G is a power of two, or the single group G == K
+      const int g = (k0 + (int)rb + 32 * h) >> p.g_shift;   // G is a power of two, or the single group G == K
       if (g != gidx[h]) {
         gidx[h] = g;
         if (ok) {
-          zq[h] = static_cast<uint32_t>(__ldg(p.qzeros + (int64_t)g * NW + wc));
-          sc[h] = __ldg(reinterpret_cast<const uint4*>(p.scales + (int64_t)g * p.N + wc * 8));
+          const uint32_t goff = (uint32_t)g * NW + wc;
+          zq[h] = static_cast<uint32_t>(__ldg(p.qzeros + goff));
+          sc[h] = __ldg(reinterpret_cast<const uint4*>(p.scales) + goff);  // 8 halves per word column
         }
       }
     }
