@@ -88,9 +88,11 @@ struct GemmLayoutLoader {
       q[j] = 0u;
       if (ok) q[j] = ldg_stream_u1(src + j * row16);
     }
-    // rows j = 0,1 (< 32) and j = 2,3 (>= 32) may sit in different groups when G == 32
+    // rows j = 0,1 (< 32) and j = 2,3 (>= 32) sit in different groups only when G == 32
+    const int nh = p.g_shift < 6 ? 2 : 1;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+      if (h >= nh) break;
       const int g = (k0 + (int)rb + 32 * h) >> p.g_shift;   // G is a power of two, or the single group G == K
       if (g != gidx[h]) {
         gidx[h] = g;
@@ -105,13 +107,18 @@ struct GemmLayoutLoader {
   __device__ __forceinline__ void store(const TcParams& p, int nt, int k0, int dt, uint32_t a_stage) const {
     const int c = dt & 15, rb = dt >> 4;
     // columns past N keep q = 0, zeros = 0, scales = 0 from init(): they dequantise to exact zeros
+    const bool two = p.g_shift < 6;  // G == 32: the two 32-row halves of the step are different groups
+    const ZeroPairs zp0 = awq_zero_pairs(zq[0]);
+    const ZeroPairs zp1 = two ? awq_zero_pairs(zq[1]) : zp0;
+    const uint4 sc1 = two ? sc[1] : sc[0];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const ZeroPairs zp = awq_zero_pairs(zq[h]);
+      const ZeroPairs& zp = h ? zp1 : zp0;
+      const uint4& sch = h ? sc1 : sc[0];
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int j = 2 * h + jj;
-        const uint4 o = awq_dequant_word(q[j], zp, sc[h]);
+        const uint4 o = awq_dequant_word(q[j], zp, sch);
         // MN-major SW128: (n/64)*8192 + (k/8)*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 ; k = rb + 16 j
         const uint32_t off = (uint32_t)(c >> 3) * 8192u + (uint32_t)(2 * j + (rb >> 3)) * 1024u +
                              (uint32_t)(rb & 7) * 128u + (uint32_t)(((c & 7) ^ (rb & 7)) << 4);
