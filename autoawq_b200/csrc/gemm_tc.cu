@@ -66,13 +66,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // GEMM layout: thread dt owns word column c = dt % 16 (8 n) and rows kk = dt/16 + 16 j, j = 0..3.
 // (A 512-thread variant with 2 rows per thread measured slower: 725 vs 838 TFLOP/s at M = 4096.)
-struct GemmLayoutLoader {
+// NG = quantisation groups per 64-row k-step: 1 for G >= 64, 2 for G == 32 (rows < 32 / >= 32).  Keeping the
+// slot small (9 registers for NG = 1) is what allows a 6-deep register prefetch ring.
+template <int NG>
+struct GemmLayoutLoaderT {
   static constexpr int kThreads = 256;
+  static constexpr int kDepth = NG == 1 ? 6 : 4;
   uint32_t q[4];
-  uint32_t zq[2];
-  uint4 sc[2];
-  int gidx[2];
-  __device__ __forceinline__ void init() { gidx[0] = gidx[1] = -1; zq[0] = zq[1] = 0; sc[0] = sc[1] = make_uint4(0, 0, 0, 0); }
+  uint32_t zq[NG];
+  uint4 sc[NG];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int h = 0; h < NG; ++h) { zq[h] = 0; sc[h] = make_uint4(0, 0, 0, 0); }
+  }
   __device__ __forceinline__ void load(const TcParams& p, int nt, int k0, int dt) {
     // 32-bit word offsets (K * N/8 < 2^32 for every real shape) keep the address arithmetic to a few
     // instructions per load; the first version spent ~90 instructions per k-step on 64-bit multiplies.
@@ -88,42 +94,30 @@ struct GemmLayoutLoader {
       q[j] = 0u;
       if (ok) q[j] = ldg_stream_u1(src + j * row16);
     }
-    // rows j = 0,1 (< 32) and j = 2,3 (>= 32) sit in different groups only when G == 32
-    const int nh = p.g_shift < 6 ? 2 : 1;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h >= nh) break;
+    for (int h = 0; h < NG; ++h) {
       const int g = (k0 + (int)rb + 32 * h) >> p.g_shift;   // G is a power of two, or the single group G == K
-      if (g != gidx[h]) {
-        gidx[h] = g;
-        if (ok) {
-          const uint32_t goff = (uint32_t)g * NW + wc;
-          zq[h] = static_cast<uint32_t>(__ldg(p.qzeros + goff));
-          sc[h] = __ldg(reinterpret_cast<const uint4*>(p.scales) + goff);  // 8 halves per word column
-        }
+      if (ok) {
+        const uint32_t goff = (uint32_t)g * NW + wc;
+        zq[h] = static_cast<uint32_t>(__ldg(p.qzeros + goff));
+        sc[h] = __ldg(reinterpret_cast<const uint4*>(p.scales) + goff);  // 8 halves per word column
       }
     }
   }
   __device__ __forceinline__ void store(const TcParams& p, int nt, int k0, int dt, uint32_t a_stage) const {
     const int c = dt & 15, rb = dt >> 4;
     // columns past N keep q = 0, zeros = 0, scales = 0 from init(): they dequantise to exact zeros
-    const bool two = p.g_shift < 6;  // G == 32: the two 32-row halves of the step are different groups
-    const ZeroPairs zp0 = awq_zero_pairs(zq[0]);
-    const ZeroPairs zp1 = two ? awq_zero_pairs(zq[1]) : zp0;
-    const uint4 sc1 = two ? sc[1] : sc[0];
+    ZeroPairs zp[NG];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const ZeroPairs& zp = h ? zp1 : zp0;
-      const uint4& sch = h ? sc1 : sc[0];
+    for (int h = 0; h < NG; ++h) zp[h] = awq_zero_pairs(zq[h]);
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int j = 2 * h + jj;
-        const uint4 o = awq_dequant_word(q[j], zp, sch);
-        // MN-major SW128: (n/64)*8192 + (k/8)*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 ; k = rb + 16 j
-        const uint32_t off = (uint32_t)(c >> 3) * 8192u + (uint32_t)(2 * j + (rb >> 3)) * 1024u +
-                             (uint32_t)(rb & 7) * 128u + (uint32_t)(((c & 7) ^ (rb & 7)) << 4);
-        sts_u4(a_stage + off, o);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const int h = NG == 1 ? 0 : (j >> 1);
+      const uint4 o = awq_dequant_word(q[j], zp[h], sc[h]);
+      // MN-major SW128: (n/64)*8192 + (k/8)*1024 + (k%8)*128 + (((n%64)/8) ^ (k%8))*16 ; k = rb + 16 j
+      const uint32_t off = (uint32_t)(c >> 3) * 8192u + (uint32_t)(2 * j + (rb >> 3)) * 1024u +
+                           (uint32_t)(rb & 7) * 128u + (uint32_t)(((c & 7) ^ (rb & 7)) << 4);
+      sts_u4(a_stage + off, o);
     }
   }
 };
@@ -131,6 +125,7 @@ struct GemmLayoutLoader {
 // GEMV layout: thread dt owns k-word cw = dt % 8 (8 consecutive k) and rows n = dt/8 + 32 j, j = 0..3.
 struct GemvLayoutLoader {
   static constexpr int kThreads = 256;
+  static constexpr int kDepth = 4;
   uint32_t q[4];
   uint32_t zs[4];  // per row: fp16 scale in the low half, zero-point (0..15) in the high half
   int gidx;
@@ -188,6 +183,7 @@ struct GemvLayoutLoader {
 // GEMVFast layout: thread dt owns row n = dt/2 of the tile and the 32-k half h = dt%2 of the step.
 struct FastLayoutLoader {
   static constexpr int kThreads = 256;
+  static constexpr int kDepth = 4;
   uint4 q;
   uint32_t ss;  // scale (low half) | scaled zero (high half)
   int gidx;
@@ -238,7 +234,8 @@ struct FastLayoutLoader {
 
 template <int LAYOUT>
 struct LoaderOf;
-template <> struct LoaderOf<0> { using T = GemmLayoutLoader; };
+template <> struct LoaderOf<0> { using T = GemmLayoutLoaderT<1>; };  // GEMM layout, G >= 64
+template <> struct LoaderOf<3> { using T = GemmLayoutLoaderT<2>; };  // GEMM layout, G == 32
 template <> struct LoaderOf<1> { using T = GemvLayoutLoader; };
 template <> struct LoaderOf<2> { using T = FastLayoutLoader; };
 
@@ -304,7 +301,7 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
       // do not depend on the predecessor kernel: this starts before the PDL wait.
       constexpr int kL2Ahead = 16;
       int wp = blockIdx.x, sp = 0, sp_end = 0;
-      bool pf_valid = (LAYOUT == 0) && p.has_tmq && wp < n_work;
+      bool pf_valid = (LAYOUT == 0 || LAYOUT == 3) && p.has_tmq && wp < n_work;
       auto pf_range = [&]() {
         const int ks = wp % p.ksplit;
         sp = (int)((int64_t)KS * ks / p.ksplit);
@@ -339,7 +336,7 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
   } else if (warp == 1) {
     // ================================================================= MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kTileN, BT, LAYOUT == 0 ? 1 : 0, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(kTileN, BT, (LAYOUT == 0 || LAYOUT == 3) ? 1 : 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -359,7 +356,7 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
 #pragma unroll
           for (int k16 = 0; k16 < kBK / 16; ++k16) {
             uint64_t da, db;
-            if (LAYOUT == 0) {
+            if (LAYOUT == 0 || LAYOUT == 3) {
               // MN-major, SW128: LBO = stride between 64-n atoms (8192), SBO = stride between 8-k atoms (1024)
               da = umma_smem_desc(a_addr + k16 * 2048, 8192, 1024);
             } else {
@@ -442,7 +439,7 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
     // ================================================================= dequant producers (8 warps)
     // Global loads run kPrefetch k-steps ahead of the dequantisation (register ring): a k-step is only
     // ~500 MMA cycles, well below the DRAM / L2 latency a 1-deep prefetch would expose every step.
-    constexpr int kPrefetch = 4;
+    constexpr int kPrefetch = LoaderOf<LAYOUT>::T::kDepth;
     const int dt = threadIdx.x - 192;  // 0..255
     const uint32_t a_base_s = smem_u32(a_base);
     typename LoaderOf<LAYOUT>::T ring[kPrefetch];
@@ -645,7 +642,7 @@ cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, 
       p.has_tmq = 1;
   }
   switch (layout) {
-    case 0: return dispatch_bt<0>(BT, tm, tmq, p, st);
+    case 0: return a.G >= 64 ? dispatch_bt<0>(BT, tm, tmq, p, st) : dispatch_bt<3>(BT, tm, tmq, p, st);
     case 1: return dispatch_bt<1>(BT, tm, tmq, p, st);
     default: return dispatch_bt<2>(BT, tm, tmq, p, st);
   }
