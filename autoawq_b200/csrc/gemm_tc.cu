@@ -128,8 +128,7 @@ struct GemvLayoutLoader {
   static constexpr int kDepth = 4;
   uint32_t q[4];
   uint32_t zs[4];  // per row: fp16 scale in the low half, zero-point (0..15) in the high half
-  int gidx;
-  __device__ __forceinline__ void init() { gidx = -1; zs[0] = zs[1] = zs[2] = zs[3] = 0; }
+  __device__ __forceinline__ void init() { zs[0] = zs[1] = zs[2] = zs[3] = 0; }
   __device__ __forceinline__ void load(const TcParams& p, int nt, int k0, int dt) {
     const int KW = p.K >> 3;
     const int cw = dt & 7, rb = dt >> 3;
@@ -140,14 +139,11 @@ struct GemvLayoutLoader {
       q[j] = 0u;
       if (n < p.N) {
         q[j] = ldg_stream_u1(p.qweight + (int64_t)n * KW + (k0 >> 3) + cw);
-        if (g != gidx) {
-          const uint32_t s = __half_as_ushort(__ldg(p.scales + (int64_t)n * (p.zw * 8) + g));
-          const uint32_t zword = static_cast<uint32_t>(__ldg(p.qzeros + (int64_t)n * p.zw + (g >> 3)));
-          zs[j] = s | (((zword >> (4 * (g & 7))) & 0xFu) << 16);
-        }
+        const uint32_t s = __half_as_ushort(__ldg(p.scales + (int64_t)n * (p.zw * 8) + g));
+        const uint32_t zword = static_cast<uint32_t>(__ldg(p.qzeros + (int64_t)n * p.zw + (g >> 3)));
+        zs[j] = s | (((zword >> (4 * (g & 7))) & 0xFu) << 16);
       }
     }
-    gidx = g;
   }
   __device__ __forceinline__ void store(const TcParams& p, int nt, int k0, int dt, uint32_t a_stage) const {
     const int cw = dt & 7, rb = dt >> 3;
@@ -186,8 +182,7 @@ struct FastLayoutLoader {
   static constexpr int kDepth = 4;
   uint4 q;
   uint32_t ss;  // scale (low half) | scaled zero (high half)
-  int gidx;
-  __device__ __forceinline__ void init() { gidx = -1; ss = 0; }
+  __device__ __forceinline__ void init() { ss = 0; }
   __device__ __forceinline__ void load(const TcParams& p, int nt, int k0, int dt) {
     const int n = nt * kTileN + (dt >> 1), h = dt & 1;
     q = make_uint4(0, 0, 0, 0);
@@ -196,13 +191,10 @@ struct FastLayoutLoader {
       // 64-k block k0/64 of row group n/4 starts at int16 offset k0; run (n%4) * 16; half h * 8
       q = ldg_stream_u4(reinterpret_cast<const int16_t*>(p.qweight) + (int64_t)(n >> 2) * p.K + (int64_t)k0 +
                         (n & 3) * 16 + h * 8);
-      if (g != gidx) {
-        const __half* sz_ptr = reinterpret_cast<const __half*>(p.qzeros);
-        ss = static_cast<uint32_t>(__half_as_ushort(__ldg(p.scales + (int64_t)g * p.N + n))) |
-             (static_cast<uint32_t>(__half_as_ushort(__ldg(sz_ptr + (int64_t)g * p.N + n))) << 16);
-      }
+      const __half* sz_ptr = reinterpret_cast<const __half*>(p.qzeros);
+      ss = static_cast<uint32_t>(__half_as_ushort(__ldg(p.scales + (int64_t)g * p.N + n))) |
+           (static_cast<uint32_t>(__half_as_ushort(__ldg(sz_ptr + (int64_t)g * p.N + n))) << 16);
     }
-    gidx = g;
   }
   __device__ __forceinline__ void store(const TcParams& p, int nt, int k0, int dt, uint32_t a_stage) const {
     const int nl = dt >> 1, h = dt & 1;
@@ -443,29 +435,53 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
     const int dt = threadIdx.x - 192;  // 0..255
     const uint32_t a_base_s = smem_u32(a_base);
     typename LoaderOf<LAYOUT>::T ring[kPrefetch];
+    // The (work item, k-step) sequence of this CTA is ONE stream: the load cursor runs kPrefetch steps ahead
+    // of the store cursor straight through tile boundaries, so the ring never drains between tiles.
+    struct Cursor {
+      int w, s, s_end, nt;
+      bool valid;
+    };
+    auto set_range = [&](Cursor& c) {
+      const int ks = c.w % p.ksplit;
+      c.nt = c.w / (p.ksplit * p.m_tiles);
+      c.s = (int)((int64_t)KS * ks / p.ksplit);
+      c.s_end = (int)((int64_t)KS * (ks + 1) / p.ksplit);
+    };
+    auto advance = [&](Cursor& c) {
+      if (++c.s == c.s_end) {
+        c.w += gridDim.x;
+        c.valid = c.w < n_work;
+        if (c.valid) set_range(c);
+      }
+    };
+    Cursor L, S;
+    L.w = S.w = blockIdx.x;
+    L.valid = S.valid = blockIdx.x < n_work;
+    if (L.valid) { set_range(L); set_range(S); }
+#pragma unroll
+    for (int d = 0; d < kPrefetch; ++d) {
+      ring[d].init();
+      if (L.valid) {
+        ring[d].load(p, L.nt, L.s * kBK, dt);
+        advance(L);
+      }
+    }
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const int ks = w % p.ksplit;
-      const int nt = w / (p.ksplit * p.m_tiles);
-      const int s_begin = (int)((int64_t)KS * ks / p.ksplit), s_end = (int)((int64_t)KS * (ks + 1) / p.ksplit);
+    while (S.valid) {
 #pragma unroll
       for (int d = 0; d < kPrefetch; ++d) {
-        ring[d].init();  // new tile: different columns, cached group data is stale
-        if (s_begin + d < s_end) ring[d].load(p, nt, (s_begin + d) * kBK, dt);
-      }
-      for (int s0 = s_begin; s0 < s_end; s0 += kPrefetch) {
-#pragma unroll
-        for (int d = 0; d < kPrefetch; ++d) {
-          const int s = s0 + d;
-          if (s < s_end) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            ring[d].store(p, nt, s * kBK, dt, a_base_s + (uint32_t)stage * kAStageBytes);
-            fence_proxy_async_smem();   // every writer: generic-proxy stores -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[stage]);  // 8 arrivals per stage instead of 256
-            if (++stage == NS) { stage = 0; phase ^= 1; }
-            if (s + kPrefetch < s_end) ring[d].load(p, nt, (s + kPrefetch) * kBK, dt);
+        if (S.valid) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          ring[d].store(p, S.nt, S.s * kBK, dt, a_base_s + (uint32_t)stage * kAStageBytes);
+          fence_proxy_async_smem();   // every writer: generic-proxy stores -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[stage]);  // 8 arrivals per stage instead of 256
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+          advance(S);
+          if (L.valid) {
+            ring[d].load(p, L.nt, L.s * kBK, dt);
+            advance(L);
           }
         }
       }
