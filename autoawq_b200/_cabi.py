@@ -18,6 +18,22 @@ _c_void_p, _c_int, _c_i64, _c_size_t, _c_float = (
     ctypes.c_float,
 )
 
+
+
+class Op(ctypes.Structure):
+    """b200awq_op_t (include/b200awq.h): one recorded operator call of a decode program."""
+
+    _fields_ = [
+        ("kind", ctypes.c_int32), ("M", ctypes.c_int32), ("K", ctypes.c_int32), ("N", ctypes.c_int32),
+        ("group_size", ctypes.c_int32), ("eps", ctypes.c_float), ("ldx", ctypes.c_int64),
+        ("x", ctypes.c_void_p), ("qweight", ctypes.c_void_p), ("scales", ctypes.c_void_p),
+        ("qzeros", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("weight", ctypes.c_void_p), ("y", ctypes.c_void_p),
+    ]
+
+
+OP_RMSNORM, OP_LINEAR_GEMM, OP_SILU_AND_MUL = 1, 2, 3
+EUNSUPPORTED = 2
+
 # name -> (restype, argtypes); mirrors include/b200awq.h one to one
 SIGNATURES = {
     "b200awq_abi_version": (_c_int, []),
@@ -45,6 +61,10 @@ SIGNATURES = {
     "b200awq_set_knob": (_c_int, [_c_int, _c_int]),
     "b200awq_get_knob": (_c_int, [_c_int]),
     "b200awq_debug_read": (_c_int, [_c_void_p, _c_size_t]),
+    "b200awq_program_create": (_c_int, [ctypes.POINTER(Op), _c_int, ctypes.POINTER(_c_void_p)]),
+    "b200awq_program_num_ops": (_c_int, [_c_void_p]),
+    "b200awq_program_run": (_c_int, [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),
+    "b200awq_program_destroy": (_c_int, [_c_void_p]),
 }
 
 

@@ -156,4 +156,33 @@ int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200aw
   return fold(silu_and_mul(gate_up, out, rows, d, static_cast<cudaStream_t>(stream)));
 }
 
+
+int b200awq_program_create(const b200awq_op_t* ops, int n_ops, b200awq_program_t* out) {
+  if (out == nullptr) return B200AWQ_EINVAL;
+  *out = nullptr;
+  Program* p = nullptr;
+  cudaError_t ce = cudaSuccess;
+  const int rc = program_create(ops, n_ops, &p, &ce);
+  if (rc == B200AWQ_ECUDA) return fold(ce);
+  if (rc != B200AWQ_OK) return rc;
+  *out = reinterpret_cast<b200awq_program_t>(p);
+  return B200AWQ_OK;
+}
+
+int b200awq_program_num_ops(b200awq_program_t prog) {
+  return prog == nullptr ? 0 : program_num_ops(reinterpret_cast<Program*>(prog));
+}
+
+int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
+  if (prog == nullptr) return B200AWQ_EINVAL;
+  Program* p = reinterpret_cast<Program*>(prog);
+  Ws ws;
+  if (!carve(workspace, workspace_bytes, program_m(p), program_max_n(p), &ws)) return B200AWQ_EWORKSPACE;
+  return fold(program_run(p, ws.acc, ws.tickets, static_cast<cudaStream_t>(stream)));
+}
+
+int b200awq_program_destroy(b200awq_program_t prog) {
+  program_destroy(reinterpret_cast<Program*>(prog));
+  return B200AWQ_OK;
+}
 }  // extern "C"

@@ -69,6 +69,21 @@ __device__ __forceinline__ int atom_add_acq_rel(int* p, int v) {
   asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
+// Cross-CTA completion counters of the decode-program kernel: producers of a result release-add after a CTA
+// barrier, consumers poll with an acquiring load (then a CTA barrier orders the rest of the CTA).
+__device__ __forceinline__ void red_release_add_s32(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ldcg_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
 __device__ __forceinline__ float ld_relaxed_f32(const float* p) {
   float v;
   asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");

@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+struct b200awq_op;
+
 namespace b200awq {
 
 struct GemmArgs {
@@ -73,6 +75,15 @@ cudaError_t gemv_fast_layout(const FastArgs& a, cudaStream_t st);
 
 // tensor-core path; layout: 0 = GEMM, 1 = GEMV, 2 = FAST (qweight/qzeros reinterpretations documented in gemm_tc.cu)
 cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, cudaStream_t st);
+
+// decode program (program.cu)
+struct Program;
+int program_create(const struct ::b200awq_op* ops, int n, Program** out, cudaError_t* cuda_err);
+int program_max_n(const Program* p);
+int program_m(const Program* p);
+int program_num_ops(const Program* p);
+cudaError_t program_run(Program* p, float* acc_ws, int* tickets, cudaStream_t st);
+void program_destroy(Program* p);
 
 cudaError_t rmsnorm(const void* x, const void* w, void* out, int rows, int hidden, float eps, cudaStream_t st);
 cudaError_t silu_and_mul(const void* gate_up, void* out, int rows, int d, cudaStream_t st);

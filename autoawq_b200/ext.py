@@ -79,8 +79,9 @@ def _check_w(t: torch.Tensor, dtype, name: str):
         raise B200AwqError(f"b200awq: {name} must be contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
 
 
-def linear_forward(layout: str, x, qweight, scales, qzeros, group_size: int, bias=None) -> torch.Tensor:
-    """Y = X . deq(W) (+ bias) for layout in {"gemm", "gemv", "fast"}; returns [M, N] fp16."""
+def linear_forward(layout: str, x, qweight, scales, qzeros, group_size: int, bias=None, out=None) -> torch.Tensor:
+    """Y = X . deq(W) (+ bias) for layout in {"gemm", "gemv", "fast"}; returns [M, N] fp16 (written into `out`
+    when given: a contiguous [M, N] fp16 tensor)."""
     _require_cuda(x, qweight, scales, qzeros, bias)
     if layout == "gemm":
         K, N = qweight.shape[0], qweight.shape[1] * 8
@@ -99,7 +100,12 @@ def linear_forward(layout: str, x, qweight, scales, qzeros, group_size: int, bia
     x2 = _x2d(x, K)
     M = x2.shape[0]
     dev = x2.device
-    y = torch.empty((M, N), dtype=torch.float16, device=dev)
+    if out is None:
+        y = torch.empty((M, N), dtype=torch.float16, device=dev)
+    else:
+        y = out
+        if y.dtype != torch.float16 or not y.is_contiguous() or y.numel() != M * N or y.device != dev:
+            raise B200AwqError("b200awq: `out` must be a contiguous float16 [M, N] tensor on the input's device")
     if M == 0:
         return y
     G = K if group_size in (-1, 0) else int(group_size)

@@ -107,6 +107,47 @@ int b200awq_get_knob(int key);
  * Synchronises the device. */
 int b200awq_debug_read(void* host_dst, size_t bytes);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Decode programs: the chain of operator calls of one decode step (M = 1), recorded once and executed by ONE
+ * persistent kernel whose weight stream runs across op boundaries (csrc/program.cu).  The op list is exactly
+ * the sequence of calls the reference's fused block makes through awq_ext (awq/modules/fused/block.py:117-170,
+ * awq/modules/fused/mlp.py:41-55): RMSNorm -> linear -> ... -> SiLU*mul -> linear.  After a run every buffer
+ * named by the ops holds what the per-op entry points above would have left there.
+ *
+ *   RMSNORM       : x = input row [K], weight [K], y = output [K], eps           (K = hidden)
+ *   SILU_AND_MUL  : x = gate|up [2K], y = output [K]                             (K = d)
+ *   LINEAR_GEMM   : as b200awq_gemm_forward (GEMM layout)
+ * b200awq_program_create returns B200AWQ_EUNSUPPORTED when the sequence does not fit the fused kernel (M != 1,
+ * a shape outside the persistent GEMV's envelope, a glue op whose output no later linear reads, aliasing the
+ * kernel's ordering cannot honour); the caller then issues the ops one by one.  Pointers are captured, not
+ * copied: the tensors must stay alive and in place for the life of the program.  Create / destroy allocate and
+ * copy (not capturable); run only enqueues a memset + one kernel on `stream` (capturable).  A program is not
+ * re-entrant: one run in flight at a time. */
+enum { B200AWQ_OP_RMSNORM = 1, B200AWQ_OP_LINEAR_GEMM = 2, B200AWQ_OP_SILU_AND_MUL = 3 };
+
+typedef struct b200awq_op {
+  int32_t kind;
+  int32_t M, K, N, group_size;
+  float eps;
+  int64_t ldx;
+  const void* x;
+  const void* qweight;
+  const void* scales;
+  const void* qzeros;
+  const void* bias;
+  const void* weight;
+  void* y;
+} b200awq_op_t;
+
+typedef struct b200awq_program* b200awq_program_t;
+
+int b200awq_program_create(const b200awq_op_t* ops, int n_ops, b200awq_program_t* out);
+/* number of fused kernel ops (= linear ops) of the program; 0 for a null handle */
+int b200awq_program_num_ops(b200awq_program_t prog);
+/* workspace: b200awq_workspace_bytes(1, K, max N over the program's linears), zero-initialised as above */
+int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
+int b200awq_program_destroy(b200awq_program_t prog);
+
 #ifdef __cplusplus
 }
 #endif
