@@ -79,7 +79,10 @@ int b200awq_set_knob(int key, int value) {
 }
 int b200awq_get_knob(int key) { return knob(key); }
 
-int b200awq_debug_read(void* host_dst, size_t bytes) { return fold(gemv_v3_debug_read(host_dst, bytes)); }
+int b200awq_debug_read(void* host_dst, size_t bytes) {
+  if (knob(3) == 2) return fold(program_debug_read(host_dst, bytes));
+  return fold(gemv_v3_debug_read(host_dst, bytes));
+}
 
 int b200awq_dequantize_gemm(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out_f16, int K,
                             int N, int group_size, b200awq_stream_t stream) {
@@ -177,8 +180,9 @@ int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspac
   if (prog == nullptr) return B200AWQ_EINVAL;
   Program* p = reinterpret_cast<Program*>(prog);
   Ws ws;
-  if (!carve(workspace, workspace_bytes, program_m(p), program_max_n(p), &ws)) return B200AWQ_EWORKSPACE;
-  return fold(program_run(p, ws.acc, ws.tickets, static_cast<cudaStream_t>(stream)));
+  // three fp32 accumulator rows of max-N columns (rounded up to 8) rotate through the ops
+  if (!carve(workspace, workspace_bytes, 3, (program_max_n(p) + 7) & ~7, &ws)) return B200AWQ_EWORKSPACE;
+  return fold(program_run(p, ws.acc, static_cast<cudaStream_t>(stream)));
 }
 
 int b200awq_program_destroy(b200awq_program_t prog) {

@@ -616,7 +616,7 @@ static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cud
   return launch_kernel(kern, dim3(grid), dim3(kV3Threads), smem, st, tm, reinterpret_cast<const __half*>(a.x), a.ldx,
                        reinterpret_cast<const __half*>(a.scales), a.qzeros, reinterpret_cast<const __half*>(a.bias),
                        reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M, a.K, a.N, a.G, g_shift,
-                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3), knob(8) > 0 ? knob(8) - 1 : 0);
+                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3) == 1 ? 1 : 0, knob(8) > 0 ? knob(8) - 1 : 0);
 }
 
 // Shapes the persistent TMA-ring kernel takes: whole 64 x 256 tiles inside one quantisation group.

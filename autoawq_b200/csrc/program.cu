@@ -12,13 +12,19 @@
 //   * producer warp: as in the persistent GEMV (gemv.cu) - lane w feeds consumer warp w's private stages with
 //     8 KB weight tiles (TMA 2-D, 128B swizzle) + the tile's group scales / zeros - but over all ops back to back;
 //     the tensor maps live in the device-resident op table;
-//   * consumers, per op: (1) wait until every column block of the previous op has been published (an acquiring
-//     poll of done[op-1]; finalising CTAs release-add to it), (2) stage the op's activations in shared memory,
-//     applying the recorded glue op on the fly - RMSNorm (each CTA recomputes the 4096-element norm from L2: 8 KB)
-//     or SiLU*mul - with the same arithmetic as the stand-alone kernels (aux.cu), (3) the tile loop / per-group
-//     fold / split-K push / ticket / finalise of the persistent GEMV, unchanged (gemv_tile.cuh).
-//   CTA 0 also writes the transformed activations to the buffer the recorded glue op named, so every tensor of
-//   the per-op path holds the same values after a program run.
+//   * consumers, per op: (1) wait until every CTA has added its split-K partial sums of the previous op (acquiring
+//     poll of done[op-1]; one release-add per CTA), (2) build the op's activations in shared memory straight from
+//     the previous op's fp32 accumulator row - fp16(acc + bias) is exactly what the per-op path stores - applying the
+//     recorded glue op on the fly (RMSNorm: every CTA recomputes the row's norm from L2, 16 KB; SiLU*mul: only the
+//     k-range of the CTA's own tiles) with the arithmetic of the stand-alone kernels (aux.cu); (3) the tile loop and
+//     per-group fold of the persistent GEMV, unchanged (gemv_tile.cuh); (4) REDs of the CTA's column sums into the
+//     op's accumulator row, one release-add.  No tickets, no finalisation pass, no fp16 round trip through memory
+//     on the critical path: first version with both measured ~10 us per op boundary
+//     (profiles/r01_program_l2ahead_sweep.md).
+//   * three accumulator rows rotate: op i adds into row i % 3, reads row (i-1) % 3, and each CTA zeroes its slice
+//     of row (i-2) % 3 (everybody finished reading it one op ago).  Every CTA also stores its slice of the previous
+//     op's fp16 output and of the glue op's output, so after a run every tensor of the per-op path holds the same
+//     values; an epilogue pass does that for the last op and leaves all rows zero.
 //
 // Reference call sequence this replaces: awq/modules/fused/block.py:117-170 (norm -> qkv -> ... -> o -> norm ->
 // mlp) with awq/modules/fused/mlp.py:41-55 (gate/up GEMM, silu*mul, down GEMM), each a separate awq_ext call.
@@ -42,25 +48,42 @@ struct __align__(128) ProgOp {
   const int32_t* qzeros;
   const __half* bias;
   __half* y;
-  const __half* src;      // COPY: x; RMSNORM: the un-normalised row; SILU: gate|up [2K]
+  const __half* src;      // external source (fp16, global) when !src_prev: COPY x, RMSNORM row, SILU gate|up
   const __half* norm_w;   // RMSNORM weight [K]
-  __half* xout;           // where the recorded glue op wanted its result (written by CTA 0), or null
-  long long ldsrc;
+  __half* xout;           // where the recorded glue op wanted its result, or null
+  int src_off;            // src_prev: first column of the previous op's output this op reads
+  int src_prev;           // 1: the source is the previous op's output, taken from its fp32 accumulators
   int K, N, G, g_shift;
   int prologue;
   float eps;
-  int ncb;                // N / 256 column blocks = completion count of this op
-  int pad;
+  int pad[2];
 };
 static_assert(sizeof(ProgOp) == 256, "ProgOp layout");
 
-constexpr int kProgSPW = 2;
-constexpr int kProgNS = kV3Warps * kProgSPW;
 constexpr int kProgMT = 1;
-constexpr size_t kProgFixedSmem = (size_t)kProgNS * (kV3TileBytes + kV3AuxBytes) +
-                                  (size_t)(kV3Warps * kProgMT * kGvRedStride + kV3Warps * kProgMT * kV3TileCols) * 4 +
-                                  2 * kProgNS * 8 + 128 + 64;
-static_assert(kProgFixedSmem % 16 == 0, "xs must stay 16-byte aligned");
+__host__ __device__ constexpr size_t prog_fixed_smem(int spw) {
+  return (size_t)kV3Warps * spw * (kV3TileBytes + kV3AuxBytes) +
+         (size_t)(kV3Warps * kProgMT * kGvRedStride + kV3Warps * kProgMT * kV3TileCols) * 4 +
+         2 * kV3Warps * spw * 8 + 128 + 64;
+}
+static_assert(prog_fixed_smem(1) % 16 == 0 && prog_fixed_smem(2) % 16 == 0, "xs must stay 16-byte aligned");
+
+// knob 3 = 2: per-op phase timestamps (globaltimer ns) of the first 8 CTAs for the first 32 kernel ops:
+// [0] op begin, [1] previous op complete (wait over), [2] activations staged, [3] first tile landed (warp 0),
+// [4] warp 0 finished its tiles, [5] all warps finished, [6] partial sums added, [7] published.
+__device__ unsigned long long g_prog_dbg[32 * 8 * 8];
+__device__ __forceinline__ unsigned long long prog_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+cudaError_t program_debug_read(void* dst, size_t bytes) {
+  return cudaMemcpyFromSymbol(dst, g_prog_dbg, bytes < sizeof(g_prog_dbg) ? bytes : sizeof(g_prog_dbg));
+}
+#define PROG_STAMP(slot)                                                                    \
+  do {                                                                                      \
+    if (dbg && ct == 0 && blockIdx.x < 8 && op < 32) g_prog_dbg[(op * 8 + blockIdx.x) * 8 + (slot)] = prog_timer(); \
+  } while (0)
 
 __device__ __forceinline__ float prog_warp_sum(float v) {
 #pragma unroll
@@ -68,10 +91,55 @@ __device__ __forceinline__ float prog_warp_sum(float v) {
   return v;
 }
 
+// 8 consecutive outputs of the previous op as the per-op path would have stored them: fp16(acc + bias)
+__device__ __forceinline__ uint4 prog_prev8(const float* __restrict__ acc, const __half* __restrict__ bias, int c) {
+  const float4 a0 = ldcg_f4(acc + c), a1 = ldcg_f4(acc + c + 4);
+  float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  if (bias != nullptr) {
+    const uint4 bv = *reinterpret_cast<const uint4*>(bias + c);
+    const __half* bh = reinterpret_cast<const __half*>(&bv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += __half2float(bh[j]);
+  }
+  uint4 r;
+  __half* rh = reinterpret_cast<__half*>(&r);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) rh[j] = __float2half_rn(v[j]);
+  return r;
+}
+
+// Wait until `cnt` reaches `target` (acquire).  Watchdog: a lost completion must surface as a launch failure,
+// never as a hung GPU.
+__device__ __forceinline__ void prog_wait(const int* cnt, int target) {
+  unsigned long long t_start = 0;
+  int spins = 0;
+  while (ld_acquire_s32(cnt) < target) {
+    if ((++spins & 1023) == 0) {
+      const unsigned long long now = prog_timer();
+      if (t_start == 0) t_start = now;
+      else if (now - t_start > 2000000000ull) __trap();
+    }
+  }
+}
+
+// mbarrier wait with the same watchdog (a TMA load that never completes must not hang the GPU)
+__device__ __forceinline__ void prog_mbar_wait(uint64_t* bar, uint32_t parity) {
+  unsigned long long t_start = 0;
+  int spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 4095) == 0) {
+      const unsigned long long now = prog_timer();
+      if (t_start == 0) t_start = now;
+      else if (now - t_start > 2000000000ull) __trap();
+    }
+  }
+}
+
+template <int SPW>
 __global__ void __launch_bounds__(kV3Threads, 1)
-    program_kernel(const ProgOp* __restrict__ ops, int n_ops, float* __restrict__ acc_ws, int* __restrict__ tickets,
-                   int* __restrict__ done, int M) {
-  constexpr int MT = kProgMT, SPW = kProgSPW, NS = kProgNS;
+    program_kernel(const ProgOp* __restrict__ ops, int n_ops, float* __restrict__ acc3, int acc_stride,
+                   int* __restrict__ done, int M, int dbg, int gate) {
+  constexpr int MT = kProgMT, NS = kV3Warps * SPW;
   extern __shared__ __align__(1024) uint8_t pg_smem[];
   uint8_t* ring = pg_smem;
   uint8_t* aux = pg_smem + (size_t)NS * kV3TileBytes;
@@ -81,11 +149,12 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   uint64_t* empty = full + NS;
   int* flags = reinterpret_cast<int*>(empty + NS);
   int* warp_cb = flags + 16;
-  int* warp_ntl = warp_cb + 8;
   float* wsum = reinterpret_cast<float*>(flags + 32);  // 8 floats (+ pad)
-  __half* xs = reinterpret_cast<__half*>(pg_smem + kProgFixedSmem);
+  volatile int* pub_op = reinterpret_cast<volatile int*>(flags + 24);  // ops this CTA has published so far
+  __half* xs = reinterpret_cast<__half*>(pg_smem + prog_fixed_smem(SPW));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nblk = gridDim.x, bid = blockIdx.x;
 
   if (tid == 0) {
     if ((smem_u32(pg_smem) & 1023u) != 0) __trap();
@@ -94,12 +163,14 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       mbar_init(&empty[s], 1);
     }
     fence_mbar_init();
+    *pub_op = 0;
   }
   for (int i = tid; i < kV3Warps * MT * kV3TileCols; i += kV3Threads) colacc[i] = 0.f;
   __syncthreads();
 
   if (warp == 0) {
     // ============================================================ producer: the weight stream of ALL ops
+    // lane w feeds consumer warp w's private stages, op after op: the ring never drains at an op boundary
     if (lane < kV3Warps) {
       const int w = lane;
       int stage_i = 0;
@@ -112,15 +183,28 @@ __global__ void __launch_bounds__(kV3Threads, 1)
         const int NW = N >> 3;
         const int TPC = K / kV3TileRows;
         const int T = (N / kV3TileCols) * TPC;
-        const int t0 = (int)((int64_t)T * blockIdx.x / gridDim.x);
-        const int t1 = (int)((int64_t)T * (blockIdx.x + 1) / gridDim.x);
+        const int t0 = (int)((int64_t)T * bid / nblk);
+        const int t1 = (int)((int64_t)T * (bid + 1) / nblk);
         const int ntile = t1 - t0;
         const int a = t0 + (int)((int64_t)ntile * w / kV3Warps);
         const int bnd = t0 + (int)((int64_t)ntile * (w + 1) / kV3Warps);
         int cb = a / TPC, kt = a - cb * TPC;
+        // gate (knob 10): this SM's REDs / release of op-1 queue behind its own outstanding bulk loads; hold the
+        // next op's loads back until they are on their way (the ring refills during the wait + staging that follow)
+        if (gate && op > 0) {
+          int spins = 0;
+          unsigned long long t_start = 0;
+          while (*pub_op < op) {
+            if ((++spins & 4095) == 0) {
+              const unsigned long long now = prog_timer();
+              if (t_start == 0) t_start = now;
+              else if (now - t_start > 2000000000ull) __trap();
+            }
+          }
+        }
         for (int t = a; t < bnd; ++t) {
           const int stage = w * SPW + stage_i;
-          mbar_wait(&empty[stage], ph ^ 1);
+          prog_mbar_wait(&empty[stage], ph ^ 1);
           const int grp_abs = (kt * kV3TileRows) >> g_shift;
           uint8_t* st = ring + (size_t)stage * kV3TileBytes;
           uint8_t* sa = aux + (size_t)stage * kV3AuxBytes;
@@ -145,42 +229,78 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   float* my_red = red + (size_t)cw * MT * kGvRedStride;
   float* my_col = colacc + (size_t)cw * MT * kV3TileCols;
   constexpr int NCT = kV3Warps * 32;
+  // this CTA's share of an n-element row, in units of 8 elements
+  auto slice8 = [&](int n, int& lo, int& hi) {
+    const int u = n >> 3;
+    lo = (int)((int64_t)u * bid / nblk) << 3;
+    hi = (int)((int64_t)u * (bid + 1) / nblk) << 3;
+  };
 
   int stage_i = 0;
   uint32_t ph = 0;
-  for (int op = 0; op < n_ops; ++op) {
-    const ProgOp* o = ops + op;
+  for (int op = 0; op <= n_ops; ++op) {
+    // op == n_ops: the epilogue pass - publish the last op's output, leave the accumulators zero
+    const bool tail = op == n_ops;
+    const ProgOp* o = ops + (tail ? n_ops - 1 : op);
+    float* A_cur = acc3 + (size_t)(op % 3) * acc_stride;          // this op's split-K sums
+    float* A_prev = acc3 + (size_t)((op + 2) % 3) * acc_stride;   // the previous op's (complete after the wait)
+    float* A_free = acc3 + (size_t)((op + 1) % 3) * acc_stride;   // read one op ago by everybody: zero it now
+
+    PROG_STAMP(0);
+    // ---- (1) every CTA has added its partial sums of the previous op
+    if (op > 0) {
+      if (ct == 0) prog_wait(&done[op - 1], nblk);
+      named_bar_sync_gv(1, NCT);
+    }
+    PROG_STAMP(1);
+
+    // ---- epilogue pass: store the last op's fp16 output, leave all accumulator rows zero
+    if (tail) {
+      const ProgOp* po = ops + op - 1;
+      int ylo, yhi, zlo, zhi;
+      slice8(po->N, ylo, yhi);
+      for (int c = ylo + ct * 8; c < yhi; c += NCT * 8)
+        *reinterpret_cast<uint4*>(po->y + c) = prog_prev8(A_prev, po->bias, c);
+      slice8(acc_stride, zlo, zhi);
+      for (int c = zlo + ct * 4; c < zhi; c += NCT * 4) *reinterpret_cast<float4*>(A_free + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      // every CTA reads only its own slice of the last row: zero exactly that slice (columns >= N are never written)
+      named_bar_sync_gv(1, NCT);
+      for (int c = ylo + ct * 4; c < yhi; c += NCT * 4) *reinterpret_cast<float4*>(A_prev + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      break;
+    }
+
     const int K = o->K, N = o->N, G = o->G, g_shift = o->g_shift;
-    const __half* bias = o->bias;
-    __half* y = o->y;
     const int TPC = K / kV3TileRows;
     const int T = (N / kV3TileCols) * TPC;
-    const int t0 = (int)((int64_t)T * blockIdx.x / gridDim.x);
-    const int t1 = (int)((int64_t)T * (blockIdx.x + 1) / gridDim.x);
+    const int t0 = (int)((int64_t)T * bid / nblk);
+    const int t1 = (int)((int64_t)T * (bid + 1) / nblk);
     const int ntile = t1 - t0;
     const int a_w = t0 + (int)((int64_t)ntile * cw / kV3Warps);
     const int b_w = t0 + (int)((int64_t)ntile * (cw + 1) / kV3Warps);
 
-    // ---- (1) the previous op's outputs are this op's inputs: wait until all its column blocks are published
-    if (op > 0) {
-      if (ct == 0) {
-        const int target = ops[op - 1].ncb;
-        while (ld_acquire_s32(&done[op - 1]) < target) {
-        }
-      }
-      named_bar_sync_gv(1, NCT);
-    }
-
-    // ---- (2) stage (and transform) the activations; arithmetic mirrors aux.cu exactly
+    // ---- (2b) stage (and transform) the activations this CTA's tiles need; arithmetic mirrors aux.cu exactly
     {
+      const bool from_prev = o->src_prev != 0;
+      const float* pa = A_prev + o->src_off;
+      const __half* pbias = (from_prev && ops[op - 1].bias != nullptr) ? ops[op - 1].bias + o->src_off : nullptr;
       const __half* src = o->src;
-      __half* xout = (blockIdx.x == 0) ? o->xout : nullptr;
+      auto load8 = [&](int c) -> uint4 { return from_prev ? prog_prev8(pa, pbias, c) : ldcg_u4(src + c); };
+      __half* xout = o->xout;
+      int xlo = 0, xhi = 0;
+      if (xout != nullptr) slice8(K, xlo, xhi);
       const int pro = o->prologue;
+      // k-range of this CTA's tiles: tiles are column-block major, so the range is contiguous modulo K
+      const int k_start = (t0 % TPC) * kV3TileRows;
+      const int k_len = ntile * kV3TileRows < K ? ntile * kV3TileRows : K;
       if (pro == kProCopy) {
-        for (int i = ct * 8; i < K; i += NCT * 8) *reinterpret_cast<uint4*>(xs + i) = ldcg_u4(src + i);
+        for (int i = ct * 8; i < k_len; i += NCT * 8) {
+          int k = k_start + i;
+          if (k >= K) k -= K;
+          *reinterpret_cast<uint4*>(xs + k) = load8(k);
+        }
       } else if (pro == kProSilu) {
-        for (int i = ct * 8; i < K; i += NCT * 8) {
-          const uint4 gv = ldcg_u4(src + i), uv = ldcg_u4(src + K + i);
+        auto silu8 = [&](int k) -> uint4 {
+          const uint4 gv = load8(k), uv = load8(K + k);
           const __half* gh = reinterpret_cast<const __half*>(&gv);
           const __half* uh = reinterpret_cast<const __half*>(&uv);
           uint4 ov;
@@ -190,20 +310,42 @@ __global__ void __launch_bounds__(kV3Threads, 1)
             const float gf = __half2float(gh[j]), uf = __half2float(uh[j]);
             oh[j] = __float2half_rn(gf / (1.f + __expf(-gf)) * uf);
           }
-          *reinterpret_cast<uint4*>(xs + i) = ov;
-          if (xout != nullptr) *reinterpret_cast<uint4*>(xout + i) = ov;
+          return ov;
+        };
+        for (int i = ct * 8; i < k_len; i += NCT * 8) {
+          int k = k_start + i;
+          if (k >= K) k -= K;
+          *reinterpret_cast<uint4*>(xs + k) = silu8(k);
         }
       } else {
+        // all of the row's loads in flight before the first use (one L2 round trip, not one per chunk pair)
         float ss = 0.f;
-        for (int i = ct * 8; i < K; i += NCT * 8) {
-          const uint4 v = ldcg_u4(src + i);
-          const __half2* h = reinterpret_cast<const __half2*>(&v);
+        uint4 nwa = make_uint4(0u, 0u, 0u, 0u), nwb = nwa;
+        for (int i = ct * 8; i < K; i += NCT * 16) {
+          const int i2 = i + NCT * 8;
+          const bool two = i2 < K;
+          const uint4 va = load8(i);
+          const uint4 vb = two ? load8(i2) : make_uint4(0u, 0u, 0u, 0u);
+          if (i < NCT * 16) {   // first pair of chunks: fetch their norm weights in the same round trip
+            nwa = __ldg(reinterpret_cast<const uint4*>(o->norm_w + i));
+            if (two) nwb = __ldg(reinterpret_cast<const uint4*>(o->norm_w + i2));
+          }
+          const __half2* ha = reinterpret_cast<const __half2*>(&va);
+          const __half2* hb = reinterpret_cast<const __half2*>(&vb);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h[j]);
+            const float2 f = __half22float2(ha[j]);
             ss += f.x * f.x + f.y * f.y;
           }
-          *reinterpret_cast<uint4*>(xs + i) = v;
+          *reinterpret_cast<uint4*>(xs + i) = va;
+          if (two) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(hb[j]);
+              ss += f.x * f.x + f.y * f.y;
+            }
+            *reinterpret_cast<uint4*>(xs + i2) = vb;
+          }
         }
         ss = prog_warp_sum(ss);
         if (lane == 0) wsum[cw] = ss;
@@ -215,17 +357,49 @@ __global__ void __launch_bounds__(kV3Threads, 1)
         const __half* nw = o->norm_w;
         for (int i = ct * 8; i < K; i += NCT * 8) {   // the thread's own chunks again
           uint4 v = *reinterpret_cast<const uint4*>(xs + i);
-          const uint4 wv = *reinterpret_cast<const uint4*>(nw + i);
+          const uint4 wv = i == ct * 8 ? nwa : (i == ct * 8 + NCT * 8 ? nwb : __ldg(reinterpret_cast<const uint4*>(nw + i)));
           __half* vh = reinterpret_cast<__half*>(&v);
           const __half* wh = reinterpret_cast<const __half*>(&wv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) vh[j] = __float2half_rn(__half2float(vh[j]) * rs * __half2float(wh[j]));
           *reinterpret_cast<uint4*>(xs + i) = v;
-          if (xout != nullptr) *reinterpret_cast<uint4*>(xout + i) = v;
+          if (i >= xlo && i < xhi) *reinterpret_cast<uint4*>(xout + i) = v;
         }
       }
       named_bar_sync_gv(1, NCT);
+
+      // ---- slice duties, off the critical path: the last consumer warp alone stores this CTA's slice of the
+      // previous op's fp16 output and of the SiLU*mul output, and recycles the accumulator row two ops back,
+      // while the other warps start on their tiles (ordered before this CTA's publish by the barriers of (4))
+      if (cw == kV3Warps - 1) {
+        if (op > 0) {
+          const ProgOp* po = ops + op - 1;
+          int ylo, yhi, zlo, zhi;
+          slice8(po->N, ylo, yhi);
+          for (int c = ylo + lane * 8; c < yhi; c += 32 * 8)
+            *reinterpret_cast<uint4*>(po->y + c) = prog_prev8(A_prev, po->bias, c);
+          slice8(acc_stride, zlo, zhi);
+          for (int c = zlo + lane * 4; c < zhi; c += 32 * 4)
+            *reinterpret_cast<float4*>(A_free + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (pro == kProSilu && xout != nullptr) {
+          for (int c = xlo + lane * 8; c < xhi; c += 32 * 8) {
+            const uint4 gv = load8(c), uv = load8(K + c);
+            const __half* gh = reinterpret_cast<const __half*>(&gv);
+            const __half* uh = reinterpret_cast<const __half*>(&uv);
+            uint4 ov;
+            __half* oh = reinterpret_cast<__half*>(&ov);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float gf = __half2float(gh[j]), uf = __half2float(uh[j]);
+              oh[j] = __float2half_rn(gf / (1.f + __expf(-gf)) * uf);
+            }
+            *reinterpret_cast<uint4*>(xout + c) = ov;
+          }
+        }
+      }
     }
+    PROG_STAMP(2);
 
     // ---- (3) the persistent-GEMV tile loop over this warp's run of tiles
     auto load_x = [&](int t, int ktile, uint32_t (&xb)[4][2]) {
@@ -261,19 +435,17 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       const int stage = cw * SPW + stage_i;
       if (cb != cur_cb) {
         if (cur_cb >= 0 && ntl > 0) {
+          // this warp's run crosses a column block: add its pending sums alone (rare)
           __syncwarp();
-          const bool fin = v3_push_warp<MT>(my_col, cur_cb, ntl, TPC, lane, bias, y, acc_ws, tickets, M, N);
-          if (fin) {
-            __syncwarp();
-            if (lane == 0) red_release_add_s32(&done[op], 1);
-          }
+          v3_add_cols<MT, 32>(my_col, 1, 0, cur_cb, lane, A_cur, M, N);
         }
         cur_cb = cb;
         ntl = 0;
       }
       ++ntl;
       load_x(t + 1, (kt + 1 == TPC) ? 0 : kt + 1, xnext);
-      mbar_wait(&full[stage], ph);
+      prog_mbar_wait(&full[stage], ph);
+      if (t == a_w) PROG_STAMP(3);
       const uint8_t* st = ring + (size_t)stage * kV3TileBytes;
       const uint8_t* sa = aux + (size_t)stage * kV3AuxBytes;
       v3_tile_mma(st, g, tig, xcur, acc, xs_acc);
@@ -293,12 +465,12 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       if (++stage_i == SPW) { stage_i = 0; ph ^= 1; }
     }
 
-    // ---- CTA-level reduction, tickets, finalisation (as gemv_v3_kernel), then publish
-    if (lane == 0) {
-      warp_cb[cw] = (ntl > 0) ? cur_cb : -1;
-      warp_ntl[cw] = ntl;
-    }
+    // ---- (4) CTA-level reduction of the per-warp column sums into this op's accumulator row, then publish:
+    // no tickets, no finalisation - the consumers of the next op read the fp32 sums themselves
+    PROG_STAMP(4);
+    if (lane == 0) warp_cb[cw] = (ntl > 0) ? cur_cb : -1;
     named_bar_sync_gv(1, NCT);
+    PROG_STAMP(5);
     {
       int w0 = 0;
       while (w0 < kV3Warps) {
@@ -306,35 +478,17 @@ __global__ void __launch_bounds__(kV3Threads, 1)
         int w1 = w0 + 1;
         while (w1 < kV3Warps && warp_cb[w1] == cbg) ++w1;
         if (cbg >= 0)
-          v3_add_cols<MT, NCT>(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cbg, ct, acc_ws, M, N);
+          v3_add_cols<MT, NCT>(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cbg, ct, A_cur, M, N);
         w0 = w1;
       }
     }
     named_bar_sync_gv(1, NCT);
-    if (ct < kV3Warps) {
-      const int w = ct;
-      const int cbg = warp_cb[w];
-      int is_last = 0;
-      if (cbg >= 0 && (w == 0 || warp_cb[w - 1] != cbg)) {
-        int tiles = 0;
-        for (int w1 = w; w1 < kV3Warps && warp_cb[w1] == cbg; ++w1) tiles += warp_ntl[w1];
-        is_last = (atom_add_acq_rel(&tickets[cbg], tiles) + tiles == TPC);
-      }
-      flags[w] = is_last;
+    PROG_STAMP(6);
+    if (ct == 0) {
+      red_release_add_s32(&done[op], 1);
+      *pub_op = op + 1;
     }
-    named_bar_sync_gv(1, NCT);
-    int nfin = 0;
-#pragma unroll 1
-    for (int w = 0; w < kV3Warps; ++w)
-      if (flags[w]) {
-        v3_finalize<MT, NCT>(warp_cb[w], ct, bias, y, acc_ws, tickets, M, N);
-        ++nfin;
-      }
-    if (nfin > 0) {   // CTA-uniform
-      named_bar_sync_gv(1, NCT);
-      if (ct == 0) red_release_add_s32(&done[op], nfin);
-    }
-    // (the barrier after the completion wait of the next op separates these shared-memory reads from its writes)
+    PROG_STAMP(7);
   }
 }
 
@@ -345,7 +499,8 @@ struct Program {
   int n_ops = 0;
   int M = 0;
   int max_N = 0;
-  size_t smem = 0;
+  int acc_stride = 0;   // floats per accumulator row (3 rows rotate through the ops)
+  size_t xs_bytes = 0;
   int device = 0;
 };
 
@@ -366,9 +521,12 @@ static bool overlaps(const void* a, size_t na, const void* b, size_t nb) {
 // Folds the recorded call sequence into linear ops with an activation prologue.  Returns a B200AWQ_* code;
 // *cuda_err carries the CUDA error behind B200AWQ_ECUDA.
 //
-// Hazard rules (the kernel orders ops only through "every column block of op i-1 is published"):
+// Hazard rules (the kernel orders ops only through "every CTA has added its sums of op i-1"; the fp16 output of
+// op i-1 and the glue output of op i are stored, in per-CTA slices, while op i stages its activations):
 //   * a glue op (RMSNorm / SiLU*mul) is executed as the prologue of every later linear that reads its output
-//     buffer; CTA 0 writes that buffer as a side effect, nobody inside the kernel may READ it;
+//     buffer; that buffer is written as a side effect, nobody inside the kernel may READ it;
+//   * a source inside the previous op's output is read from that op's fp32 accumulators (src_prev); any other
+//     overlap with the previous op's output is rejected; outputs older than that are ordinary global reads;
 //   * a linear must not write (y) what it reads (src) or what its own prologue publishes (xout);
 //   * a buffer that a pending glue record depends on must not be overwritten before the record's last use.
 int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* cuda_err) {
@@ -441,8 +599,6 @@ int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* c
       p.g_shift = 0;
       while ((1 << p.g_shift) < p.G) ++p.g_shift;
     }
-    p.ncb = op.N / kV3TileCols;
-    p.ldsrc = op.ldx;
     Glue* hit = nullptr;
     for (Glue& gl : glues)
       if (gl.live && gl.out == op.x && gl.width == op.K) hit = &gl;
@@ -463,6 +619,20 @@ int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* c
     const size_t src_bytes = (size_t)(p.prologue == kProSilu ? 2 : 1) * op.K * 2;
     if (overlaps(p.y, (size_t)op.N * 2, p.src, src_bytes)) return B200AWQ_EUNSUPPORTED;
     if (p.xout != nullptr && overlaps(p.xout, (size_t)op.K * 2, p.y, (size_t)op.N * 2)) return B200AWQ_EUNSUPPORTED;
+    if (!table.empty()) {
+      // the previous op's fp16 output reaches memory only while THIS op stages its activations: a source inside it
+      // is taken from the previous op's fp32 accumulators instead (same values), anything else touching it is a race
+      const ProgOp& pv = table.back();
+      const uintptr_t y0 = reinterpret_cast<uintptr_t>(pv.y), s0 = reinterpret_cast<uintptr_t>(p.src);
+      if (s0 >= y0 && s0 + src_bytes <= y0 + (size_t)pv.N * 2) {
+        if (((s0 - y0) & 15) != 0) return B200AWQ_EUNSUPPORTED;
+        p.src_prev = 1;
+        p.src_off = static_cast<int>((s0 - y0) / 2);
+      } else if (overlaps(pv.y, (size_t)pv.N * 2, p.src, src_bytes)) {
+        return B200AWQ_EUNSUPPORTED;
+      }
+      if (p.xout != nullptr && overlaps(p.xout, (size_t)op.K * 2, pv.y, (size_t)pv.N * 2)) return B200AWQ_EUNSUPPORTED;
+    }
     // writing y over something a live glue record still needs ends that record
     for (Glue& gl : glues)
       if (gl.live && &gl != hit &&
@@ -478,20 +648,23 @@ int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* c
   for (const Glue& gl : glues)
     if (!gl.used) return B200AWQ_EUNSUPPORTED;   // a glue op nobody consumes would never run
   if (table.empty()) return B200AWQ_EUNSUPPORTED;
-  const size_t smem = kProgFixedSmem + (size_t)(max_K + 8) * 2 * kProgMT;
+  const size_t smem = prog_fixed_smem(2) + (size_t)(max_K + 8) * 2 * kProgMT;
   if (smem > (size_t)227 * 1024) return B200AWQ_EUNSUPPORTED;
 
   Program* pr = new Program();
   pr->n_ops = static_cast<int>(table.size());
   pr->M = M;
   pr->max_N = max_N;
-  pr->smem = smem;
+  pr->acc_stride = (max_N + 7) & ~7;
+  pr->xs_bytes = (size_t)(max_K + 8) * 2 * kProgMT;
   cudaError_t e = cudaGetDevice(&pr->device);
   if (e == cudaSuccess) e = cudaMalloc(&pr->d_ops, table.size() * sizeof(ProgOp));
-  if (e == cudaSuccess) e = cudaMalloc(&pr->d_done, table.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&pr->d_done, (table.size() + 1) * sizeof(int));
   if (e == cudaSuccess) e = cudaMemcpy(pr->d_ops, table.data(), table.size() * sizeof(ProgOp), cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    e = cudaFuncSetAttribute(program_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(program_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
   if (e != cudaSuccess) {
     cudaFree(pr->d_ops);
     cudaFree(pr->d_done);
@@ -507,13 +680,14 @@ int program_max_n(const Program* p) { return p->max_N; }
 int program_m(const Program* p) { return p->M; }
 int program_num_ops(const Program* p) { return p->n_ops; }
 
-cudaError_t program_run(Program* p, float* acc_ws, int* tickets, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(p->d_done, 0, (size_t)p->n_ops * sizeof(int), st);
+cudaError_t program_run(Program* p, float* acc_ws, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(p->d_done, 0, (size_t)(p->n_ops + 1) * sizeof(int), st);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(prog_sm_count());
   cfg.blockDim = dim3(kV3Threads);
-  cfg.dynamicSmemBytes = p->smem;
+  const int spw = knob(9) == 1 ? 1 : 2;
+  cfg.dynamicSmemBytes = prog_fixed_smem(spw) + p->xs_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the completion counters are grid-wide waits
@@ -521,7 +695,10 @@ cudaError_t program_run(Program* p, float* acc_ws, int* tickets, cudaStream_t st
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const ProgOp* ops = p->d_ops;
-  return cudaLaunchKernelEx(&cfg, program_kernel, ops, p->n_ops, acc_ws, tickets, p->d_done, p->M);
+  const int dbg = knob(3) == 2 ? 1 : 0, gate = knob(10) == 2 ? 0 : 1;   // gate on unless knob 10 == 2
+  if (spw == 1)
+    return cudaLaunchKernelEx(&cfg, program_kernel<1>, ops, p->n_ops, acc_ws, p->acc_stride, p->d_done, p->M, dbg, gate);
+  return cudaLaunchKernelEx(&cfg, program_kernel<2>, ops, p->n_ops, acc_ws, p->acc_stride, p->d_done, p->M, dbg, gate);
 }
 
 void program_destroy(Program* p) {

@@ -125,20 +125,22 @@ class Replica:
         self.out = torch.empty((M, HIDDEN), dtype=torch.float16, device=dev)
         self.launches_per_step = layers * 7
 
-    def lin(self, x, w):
+    def lin(self, x, w, api=None):
         # the awq_ext-facing operator (awq_ext.gemm_forward_cuda semantics; autoawq_b200/ext.py)
-        return self.ext.gemm_forward_cuda(x, w[0], w[1], w[2], 8)
+        return (api or self.ext).gemm_forward_cuda(x, w[0], w[1], w[2], 8)
 
-    def step(self, h):
-        e = self.ext
+    def step(self, h, api=None):
+        """The operator-call sequence of one step.  `api` = the awq_ext surface (default) or a DecodeProgram
+        recorder with the same call names (autoawq_b200/program.py)."""
+        e = api or self.ext
         for lw in self.w:
             e.layernorm_forward_cuda(h, self.norm_w, self.xn, 1e-5)
-            qkv = self.lin(self.xn, lw["qkv"])
-            o = self.lin(qkv[:, :HIDDEN], lw["o"])
+            qkv = self.lin(self.xn, lw["qkv"], e)
+            o = self.lin(qkv[:, :HIDDEN], lw["o"], e)
             e.layernorm_forward_cuda(o, self.norm_w, self.xn, 1e-5)
-            gu = self.lin(self.xn, lw["gate_up"])
+            gu = self.lin(self.xn, lw["gate_up"], e)
             e.silu_and_mul(self.act, gu)
-            h = self.lin(self.act, lw["down"])
+            h = self.lin(self.act, lw["down"], e)
         return h
 
     def gemm_only(self, h):
@@ -239,6 +241,10 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--pdl", type=int, default=1, help="1: launch kernels with programmatic dependent launch")
     ap.add_argument("--nextw", type=int, default=0, help="1: learned next-weight L2 prefetch (knob 6)")
+    ap.add_argument("--knob", action="append", default=[], help="debug: KEY=VALUE library knob (repeatable)")
+    ap.add_argument("--program", type=int, default=1,
+                    help="decode: 1 = record the step once and run it as ONE persistent kernel (b200awq_program_*); "
+                         "0 = one kernel launch per operator call")
     ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: fewer layers => INVALID as a bench value")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -300,12 +306,41 @@ def main():
     rep = Replica(dev, M, layers=a.layers, seed=rank)
     rep.ext.set_knob(4, 1 if a.pdl else 0)
     rep.ext.set_knob(6, 1 if a.nextw else 0)
+    for kv in a.knob:
+        k, v = kv.split("=")
+        rep.ext.set_knob(int(k), int(v))
+        config.setdefault("knobs", {})[k] = int(v)
     config["pdl"] = bool(a.pdl)
     config["next_weight_l2_prefetch"] = bool(a.nextw)
     peaks = measured_peaks()
 
+    # the step as ONE persistent kernel (decode): same operator calls, recorded once through the recorder that
+    # mirrors the awq_ext call names, replayed by b200awq_program_run
+    prog = None
+    if a.mode == "decode" and a.program:
+        from autoawq_b200.program import DecodeProgram
+
+        prog = DecodeProgram()
+        prog_out = rep.step(rep.h, api=prog)
+        prog.build()
+        if not prog.fused:
+            prog = None
+
+    # per-op path: the step replayed as one CUDA graph of 224 kernel launches
+    g_ops, out_ops = capture(torch, lambda: rep.step(rep.h))
+    per_op = None
+    if prog is not None:
+        sec_ops = timed(torch, g_ops.replay, a.steps, a.warmup, dist)
+        per_op = {"tok_s": round(world * tokens_per_step * a.steps / sec_ops, 2),
+                  "ms_per_step": round(sec_ops / a.steps * 1e3, 4), "launches_per_step": rep.launches_per_step}
+        g_step, _ = capture(torch, prog.run)
+        out_static = prog_out
+        launches_per_step = 1
+    else:
+        g_step, out_static = g_ops, out_ops
+        launches_per_step = rep.launches_per_step
+
     # value leg: inputs resident in HBM, the step replayed as one CUDA graph
-    g_step, out_static = capture(torch, lambda: rep.step(rep.h))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -322,7 +357,27 @@ def main():
     alg_bytes = sum(linear_bytes(K, N, M) for _, K, N in LINEARS) * a.layers
     alg_flops = sum(2.0 * M * K * N for _, K, N in LINEARS) * a.layers
     avg_launch_s = sec_lin / a.steps / n_lin
-    if a.mode == "decode":
+    if prog is not None:
+        # the dominant (only) kernel is the program kernel: one launch streams every linear of the step
+        step_s = sec / a.steps
+        ach = alg_bytes / step_s / 1e9
+        lin_ach = alg_bytes / n_lin / avg_launch_s / 1e9
+        per_op["linear_avg_us"] = round(avg_launch_s * 1e6, 2)
+        per_op["linear_gbs"] = round(lin_ach, 1)
+        per_op["linear_frac"] = round(lin_ach / peaks["hbm_gbs"], 4)
+        roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(ach / peaks["hbm_gbs"], 4),
+                # dram__bytes_read + write per program_kernel launch: profiles/r01_ncu_program_kernel_bench.csv
+                # (3,626.4 MB read + 9-14 MB written; algorithmic 3,626 MB)
+                "traffic": 3638000000 if a.layers == LAYERS else None,
+                "kernel": "program_kernel (persistent decode program: 128 linears + glue per launch)",
+                "peak_src": peaks["src"] + " (hbm_gbs)",
+                "per_launch": {"avg_us": round(step_s * 1e6, 2), "alg_bytes": alg_bytes,
+                               "launches_timed": a.steps,
+                               "how": "CUDA events around graph replays of b200awq_program_run (memset + kernel); "
+                                      "algorithmic bytes = packed weights + scales + zeros + activations of all "
+                                      "128 linears"}}
+    elif a.mode == "decode":
         ach = alg_bytes / n_lin / avg_launch_s / 1e9
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(ach / peaks["hbm_gbs"], 4),
@@ -358,7 +413,11 @@ def main():
     # eager plugin calls (no graph): what a Python caller that does not capture graphs sees
     def eager_step():
         rep.h.copy_(h_host, non_blocking=True)
-        y = rep.step(rep.h)
+        if prog is not None:
+            prog.run()
+            y = prog_out
+        else:
+            y = rep.step(rep.h)
         y_host.copy_(y, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -377,14 +436,19 @@ def main():
         cpu = {"value": m_eff / (t_layer * LAYERS), "unit": "tok/s", "cores": cores, "kind": "port",
                "sample": f"1 of 32 layers (4 linears, dequantize_gemm + torch.matmul fp16, M={m_eff}), best of 2, x32"}
     config["e2e_eager_tok_s"] = round(world * tokens_per_step * n_eager / sec_eager, 1)
-    config["value_leg"] = "CUDA-graph replay of the awq_ext-facing operator calls, inputs resident in HBM"
+    if prog is not None:
+        config["value_leg"] = ("CUDA-graph replay of b200awq_program_run: the step's awq_ext-facing operator calls "
+                               "recorded once, executed as one persistent kernel; inputs resident in HBM")
+        config["per_op_path"] = per_op
+    else:
+        config["value_leg"] = "CUDA-graph replay of the awq_ext-facing operator calls, inputs resident in HBM"
     line = {"metric": metric, "value": round(value, 2), "unit": "tok/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(sec / a.steps * 1e3, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config,
             "clocks": clocks,
             "e2e": {"value": round(e2e_val, 2), "unit": "tok/s", "h2d_bytes_per_step": M * HIDDEN * 2,
                     "d2h_bytes_per_step": M * HIDDEN * 2},
-            "gpu_launches": rep.launches_per_step * a.steps,
+            "gpu_launches": launches_per_step * a.steps,
             "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if dist is not None:

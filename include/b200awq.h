@@ -88,7 +88,10 @@ int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200aw
  *   key 0: GEMV rows per warp override: 32 / 64 / 128 (0 = heuristic)
  *   key 1: tensor-core path split-K override (0 = heuristic)
  *   key 2: M threshold at or below which the CUDA-core GEMV is used (default 8)
- *   key 3: 1 = the persistent GEMV records per-CTA phase timestamps (read with b200awq_debug_read)
+ *   key 3: 1 = the persistent GEMV records per-CTA phase timestamps (read with b200awq_debug_read);
+ *          2 = the decode-program kernel records per-op phase timestamps of its first 8 CTAs / 32 ops
+ *          (b200awq_debug_read then returns [op][cta][8] uint64 ns: op begin, previous op complete, activations
+ *          staged, first tile landed, warp 0 done, all warps done, partial sums added, published)
  *   key 4: 1 = launch every kernel with the programmatic-dependent-launch attribute (the kernels issue
  *          their weight loads before griddepcontrol.wait, so consecutive linears overlap); default 0
  *   key 5: 1 = disable the persistent TMA-ring GEMV (use the register-staged GEMV for every M <= 8 shape)
@@ -144,7 +147,8 @@ typedef struct b200awq_program* b200awq_program_t;
 int b200awq_program_create(const b200awq_op_t* ops, int n_ops, b200awq_program_t* out);
 /* number of fused kernel ops (= linear ops) of the program; 0 for a null handle */
 int b200awq_program_num_ops(b200awq_program_t prog);
-/* workspace: b200awq_workspace_bytes(1, K, max N over the program's linears), zero-initialised as above */
+/* workspace: b200awq_workspace_bytes(3, K, max N over the program's linears rounded up to 8): three fp32
+ * accumulator rows; zero-initialised and left all-zero like the per-op workspace (the same buffer may serve both) */
 int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
 int b200awq_program_destroy(b200awq_program_t prog);
 

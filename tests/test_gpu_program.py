@@ -1,0 +1,224 @@
+"""GPU tests of the decode-program kernel (csrc/program.cu) through the C ABI (b200awq_program_*): every buffer a
+program run leaves behind is checked, op by op, against the CPU oracle applied to the op's ACTUAL input (the
+buffer the previous op left on the GPU) - so each recorded op is held to the same bar as the stand-alone entry
+points (tests/test_gpu_parity.py) - and against the per-op path run on the same inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import awq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2.0**-10
+WR_GEMV = 2.0**-11
+EPS = 1e-5
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(_dev())
+
+
+def _close(y, ref64, budget, what):
+    y = np.asarray(y, dtype=np.float64)
+    tol = RTOL * np.abs(ref64) + WR_GEMV * budget + 1e-6
+    bad = np.abs(y - ref64) > tol
+    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} outside tolerance, max err {np.abs(y - ref64).max():.3e}"
+
+
+class Block:
+    """One Llama-style block's quantised linears (random AWQ-packed weights) + its call sequence."""
+
+    def __init__(self, hidden, inter, qkv_out, G, seed):
+        self.hidden, self.inter, self.G = hidden, inter, G
+        shapes = dict(qkv=(hidden, qkv_out), o=(hidden, hidden), gate_up=(hidden, 2 * inter), down=(inter, hidden))
+        self.np, self.w = {}, {}
+        rng = np.random.default_rng(seed)
+        for i, (name, (K, N)) in enumerate(shapes.items()):
+            c = O.make_case(K, N, G, seed=seed * 10 + i)
+            # scales sized so activations stay O(1) along the chain
+            sc = (c["scales"].astype(np.float32) * (1.0 / (6.1 * 0.0108 * np.sqrt(K)))).astype(np.float16)
+            self.np[name] = dict(qweight=c["qweight"], qzeros=c["qzeros"], scales=sc,
+                                 w=O.dequantize_gemm(c["qweight"], c["qzeros"], sc, G))
+            self.w[name] = (_t(c["qweight"]), _t(sc), _t(c["qzeros"]))
+        self.norm1 = (1 + 0.1 * rng.standard_normal(hidden)).astype(np.float16)
+        self.norm2 = (1 + 0.1 * rng.standard_normal(hidden)).astype(np.float16)
+        self.norm1_t, self.norm2_t = _t(self.norm1), _t(self.norm2)
+
+
+def _record(api, blocks, h, M):
+    """The bench's / fused block's call sequence against `api` (awq_ext-like).  Returns every buffer by name."""
+    bufs = []
+    for b in blocks:
+        xn = torch.empty((M, b.hidden), dtype=torch.float16, device=_dev())
+        api.layernorm_forward_cuda(h, b.norm1_t, xn, EPS)
+        qkv = api.gemm_forward_cuda(xn, *b.w["qkv"], 8)
+        o = api.gemm_forward_cuda(qkv[:, : b.hidden], *b.w["o"], 8)
+        xn2 = torch.empty((M, b.hidden), dtype=torch.float16, device=_dev())
+        api.layernorm_forward_cuda(o, b.norm2_t, xn2, EPS)
+        gu = api.gemm_forward_cuda(xn2, *b.w["gate_up"], 8)
+        act = torch.empty((M, b.inter), dtype=torch.float16, device=_dev())
+        api.silu_and_mul(act, gu)
+        down = api.gemm_forward_cuda(act, *b.w["down"], 8)
+        bufs.append(dict(h=h, xn=xn, qkv=qkv, o=o, xn2=xn2, gu=gu, act=act, down=down))
+        h = down
+    return bufs
+
+
+def _check_against_oracle(blocks, bufs, tag):
+    for li, (b, t) in enumerate(zip(blocks, bufs)):
+        v = {k: x.float().cpu().numpy().astype(np.float16) for k, x in t.items()}
+        np.testing.assert_allclose(v["xn"], O.rmsnorm_f64(v["h"], b.norm1, EPS), rtol=2e-3, atol=2e-3,
+                                   err_msg=f"{tag} L{li} norm1")
+        np.testing.assert_allclose(v["xn2"], O.rmsnorm_f64(v["o"], b.norm2, EPS), rtol=2e-3, atol=2e-3,
+                                   err_msg=f"{tag} L{li} norm2")
+        g64 = v["gu"][:, : b.inter].astype(np.float64)
+        np.testing.assert_allclose(v["act"], g64 / (1 + np.exp(-g64)) * v["gu"][:, b.inter:].astype(np.float64),
+                                   rtol=2e-3, atol=2e-3, err_msg=f"{tag} L{li} silu")
+        for name, xin, yout in [("qkv", v["xn"], v["qkv"]), ("o", v["qkv"][:, : b.hidden], v["o"]),
+                                ("gate_up", v["xn2"], v["gu"]), ("down", v["act"], v["down"])]:
+            w = b.np[name]["w"]
+            budget = np.abs(xin.astype(np.float64)) @ np.abs(w.astype(np.float64))
+            _close(yout, O.gemm_f64(xin, w), budget, f"{tag} L{li} {name}")
+
+
+@pytest.fixture(scope="module")
+def api():
+    import awq_ext  # noqa: F401
+    from autoawq_b200 import ext
+
+    return ext
+
+
+@pytest.fixture(scope="module")
+def small_blocks():
+    return [Block(2048, 4096, 3072, 128, seed=s) for s in (1, 2)]
+
+
+def _h0(hidden, M, seed=0):
+    return _t(np.random.default_rng(seed).standard_normal((M, hidden)).astype(np.float16))
+
+
+def test_program_matches_oracle_op_by_op(api, small_blocks):
+    from autoawq_b200.program import DecodeProgram
+
+    h = _h0(2048, 1)
+    prog = DecodeProgram()
+    bufs = _record(prog, small_blocks, h, 1)
+    prog.build()
+    assert prog.fused and prog.kernel_ops == 8 and prog.launches_per_run == 1
+    prog.run()
+    torch.cuda.synchronize()
+    _check_against_oracle(small_blocks, bufs, "program")
+    # the per-op path on the same inputs: same arithmetic up to fp32 summation order
+    ref = _record(api, small_blocks, h, 1)
+    # (loose: the two paths add their fp32 partial sums in different orders, and the difference of one fp16 ulp
+    # propagates down the chain; the op-by-op oracle check above is the parity gate)
+    for a, b in zip(bufs, ref):
+        for k in a:
+            assert torch.allclose(a[k].float(), b[k].float(), rtol=3e-2, atol=3e-2), k
+    # identical input -> the rmsnorm prologue reproduces the stand-alone kernel bit for bit (later ops see inputs
+    # that differ in the last bit: fp32 atomics order)
+    assert torch.equal(bufs[0]["xn"], ref[0]["xn"])
+
+
+def test_program_replays_and_leaves_scratch_clean(api, small_blocks):
+    from autoawq_b200.program import DecodeProgram
+
+    h = _h0(2048, 1, seed=3)
+    prog = DecodeProgram()
+    bufs = _record(prog, small_blocks, h, 1)
+    prog.build()
+    assert prog.fused
+    prog.run()
+    first = {k: v.clone() for k, v in bufs[-1].items()}
+    for _ in range(5):
+        prog.run()
+    torch.cuda.synchronize()
+    for k, v in bufs[-1].items():
+        assert torch.allclose(v.float(), first[k].float(), rtol=3e-2, atol=3e-2), k
+    # new input in place -> new output; then the per-op entry points still find an all-zero workspace
+    h.copy_(_h0(2048, 1, seed=4))
+    prog.run()
+    torch.cuda.synchronize()
+    _check_against_oracle(small_blocks, bufs, "program replay")
+    ref = _record(api, small_blocks, h, 1)
+    torch.cuda.synchronize()
+    _check_against_oracle(small_blocks, ref, "per-op after program")
+    for ws in api._WS.values():
+        assert int(ws.count_nonzero()) == 0, "program left the shared workspace dirty"
+
+
+def test_program_in_cuda_graph(api, small_blocks):
+    from autoawq_b200.program import DecodeProgram
+
+    h = _h0(2048, 1, seed=5)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        prog = DecodeProgram()
+        bufs = _record(prog, small_blocks, h, 1)
+        prog.build()
+        prog.run()  # allocates the stream's workspace outside the capture
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            prog.run()
+        h.copy_(_h0(2048, 1, seed=6))
+        g.replay()
+        s.synchronize()
+    torch.cuda.synchronize()
+    _check_against_oracle(small_blocks, bufs, "program graph replay")
+
+
+def test_program_falls_back_per_op_when_not_fusable(api, small_blocks):
+    from autoawq_b200.program import DecodeProgram
+
+    h = _h0(2048, 2, seed=7)  # M = 2: outside the fused kernel's envelope
+    prog = DecodeProgram()
+    bufs = _record(prog, small_blocks[:1], h, 2)
+    prog.build()
+    assert not prog.fused and prog.launches_per_run == 7
+    prog.run()
+    torch.cuda.synchronize()
+    _check_against_oracle(small_blocks[:1], bufs, "program (per-op replay)")
+
+
+def test_program_rejects_unconsumed_glue_and_aliasing(api, small_blocks):
+    from autoawq_b200.program import DecodeProgram
+
+    b = small_blocks[0]
+    h = _h0(2048, 1)
+    xn = torch.empty_like(h)
+    p = DecodeProgram()
+    p.layernorm_forward_cuda(h, b.norm1_t, xn, EPS)   # nobody reads xn
+    p.gemm_forward_cuda(h, *b.w["qkv"], 8)
+    p.build()
+    assert not p.fused
+    p2 = DecodeProgram()
+    p2.layernorm_forward_cuda(h, b.norm1_t, xn, EPS)
+    p2.gemm_forward_cuda(xn, *b.w["qkv"], 8)
+    p2.gemm_forward_cuda(xn, *b.w["o"], 8)            # second reader of the same norm output: prologue re-applied
+    p2.build()
+    assert p2.fused and p2.kernel_ops == 2
+    p2.run()
+    torch.cuda.synchronize()
+
+
+def test_program_llama8b_layer_shapes(api):
+    """BASELINE config 2 shapes (Llama-3-8B, g128): two full-size blocks, program vs oracle op by op."""
+    from autoawq_b200.program import DecodeProgram
+
+    blocks = [Block(4096, 14336, 6144, 128, seed=s) for s in (11, 12)]
+    h = _h0(4096, 1, seed=9)
+    prog = DecodeProgram()
+    bufs = _record(prog, blocks, h, 1)
+    prog.build()
+    assert prog.fused and prog.kernel_ops == 8
+    for _ in range(3):
+        prog.run()
+    torch.cuda.synchronize()
+    _check_against_oracle(blocks, bufs, "program 8B shapes")
