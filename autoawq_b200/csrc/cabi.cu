@@ -81,6 +81,7 @@ int b200awq_get_knob(int key) { return knob(key); }
 
 int b200awq_debug_read(void* host_dst, size_t bytes) {
   if (knob(3) == 2) return fold(program_debug_read(host_dst, bytes));
+  if (knob(3) == 3) return fold(program_abort_read(host_dst, bytes));
   return fold(gemv_v3_debug_read(host_dst, bytes));
 }
 
@@ -180,8 +181,8 @@ int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspac
   if (prog == nullptr) return B200AWQ_EINVAL;
   Program* p = reinterpret_cast<Program*>(prog);
   Ws ws;
-  // three fp32 accumulator rows of max-N columns (rounded up to 8) rotate through the ops
-  if (!carve(workspace, workspace_bytes, 3, (program_max_n(p) + 7) & ~7, &ws)) return B200AWQ_EWORKSPACE;
+  // four rows of 64-bit packed sums (= 8 floats per column), max-N columns rounded up to 8, rotate through the ops
+  if (!carve(workspace, workspace_bytes, 8, (program_max_n(p) + 7) & ~7, &ws)) return B200AWQ_EWORKSPACE;
   return fold(program_run(p, ws.acc, static_cast<cudaStream_t>(stream)));
 }
 

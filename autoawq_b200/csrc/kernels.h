@@ -85,6 +85,7 @@ int program_num_ops(const Program* p);
 cudaError_t program_run(Program* p, float* acc_ws, cudaStream_t st);
 void program_destroy(Program* p);
 cudaError_t program_debug_read(void* dst, size_t bytes);
+cudaError_t program_abort_read(void* dst, size_t bytes);
 
 cudaError_t rmsnorm(const void* x, const void* w, void* out, int rows, int hidden, float eps, cudaStream_t st);
 cudaError_t silu_and_mul(const void* gate_up, void* out, int rows, int d, cudaStream_t st);

@@ -56,7 +56,8 @@ struct __align__(128) ProgOp {
   int K, N, G, g_shift;
   int prologue;
   float eps;
-  int pad[2];
+  int ext_dep;            // >= 0: the external source was written by that (older) op of this program
+  int pad;
 };
 static_assert(sizeof(ProgOp) == 256, "ProgOp layout");
 
@@ -82,7 +83,7 @@ cudaError_t program_debug_read(void* dst, size_t bytes) {
 }
 #define PROG_STAMP(slot)                                                                    \
   do {                                                                                      \
-    if (dbg && ct == 0 && blockIdx.x < 8 && op < 32) g_prog_dbg[(op * 8 + blockIdx.x) * 8 + (slot)] = prog_timer(); \
+    if (dbg == 2 && ct == 0 && blockIdx.x < 8 && op < 32) g_prog_dbg[(op * 8 + blockIdx.x) * 8 + (slot)] = prog_timer(); \
   } while (0)
 
 __device__ __forceinline__ float prog_warp_sum(float v) {
@@ -91,54 +92,146 @@ __device__ __forceinline__ float prog_warp_sum(float v) {
   return v;
 }
 
-// 8 consecutive outputs of the previous op as the per-op path would have stored them: fp16(acc + bias)
-__device__ __forceinline__ uint4 prog_prev8(const float* __restrict__ acc, const __half* __restrict__ bias, int c) {
-  const float4 a0 = ldcg_f4(acc + c), a1 = ldcg_f4(acc + c + 4);
-  float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+// ---------------------------------------------------------------------------------- packed split-K hand-off
+// One 64-bit word per output column carries the sum AND its own completion state:
+//     word = (tiles contributed << 48) | sum of (v_fixed + tiles * 2^39),   v_fixed = round(v * 2^24)
+// Every push is a single red.add.u64, so a reader that sees tiles == K/64 holds the complete sum - no counter to
+// publish after the data, no acknowledgement to wait for, no acquire before reading it: the chain between two
+// ops is one RED (one way) plus one polling load.  Integer addition also makes the result independent of the
+// order in which CTAs arrive: a program run is bit-reproducible.
+// Range: |partial sum| is clamped to tiles * 32768 (fp16 outputs beyond that are inf anyway); resolution 2^-24
+// (one fp16 subnormal step, below the fp32 rounding of the per-op path for |y| >= 1); K/64 < 256 tiles per column.
+constexpr int kProgRows = 4;              // accumulator rows in rotation (see the reclamation protocol below)
+static_assert(kProgRows == 4, "prog_wait_row_clean hard-codes the rotation depth");
+constexpr float kFixScale = 16777216.0f;  // 2^24
+__device__ __forceinline__ unsigned long long prog_pack(float v, int ntl) {
+  long long f = __float2ll_rn(v * kFixScale);
+  const long long lim = ((long long)ntl << 39) - 1;
+  f = f > lim ? lim : (f < -lim ? -lim : f);
+  return ((unsigned long long)ntl << 48) + (unsigned long long)(((long long)ntl << 39) + f);
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Polling load: STRONG (relaxed at gpu scope), not a weak load with a cache hint - the rows are polled without any
+// acquire in front, and a weak ld.cg may keep returning a stale copy from the near L2 partition for ever (seen on
+// B200: the duty warps spun on complete rows).
+__device__ __forceinline__ ulonglong2 ldcg_u64x2(const unsigned long long* p) {
+  ulonglong2 r;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+  return r;
+}
+// 8 consecutive outputs of the previous op as the per-op path would have stored them, fp16(sum + bias);
+// ok = false while any of the 8 columns is still missing contributions (TPC = the previous op's K / 64)
+__device__ __forceinline__ bool prog_prev8(const unsigned long long* __restrict__ row, const __half* __restrict__ bias,
+                                           int c, int TPC, uint4& out) {
+  const ulonglong2 w0 = ldcg_u64x2(row + c), w1 = ldcg_u64x2(row + c + 2), w2 = ldcg_u64x2(row + c + 4),
+                   w3 = ldcg_u64x2(row + c + 6);
+  const unsigned long long w[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
+  bool ok = true;
+  float v[8];
+  const long long off = (long long)TPC << 39;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ok = ok && (int)(w[j] >> 48) == TPC;
+    v[j] = __ll2float_rn((long long)(w[j] & 0xFFFFFFFFFFFFull) - off) * (1.0f / kFixScale);
+  }
   if (bias != nullptr) {
     const uint4 bv = *reinterpret_cast<const uint4*>(bias + c);
     const __half* bh = reinterpret_cast<const __half*>(&bv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] += __half2float(bh[j]);
   }
-  uint4 r;
-  __half* rh = reinterpret_cast<__half*>(&r);
+  __half* rh = reinterpret_cast<__half*>(&out);
 #pragma unroll
   for (int j = 0; j < 8; ++j) rh[j] = __float2half_rn(v[j]);
-  return r;
+  return ok;
 }
 
-// Wait until `cnt` reaches `target` (acquire).  Watchdog: a lost completion must surface as a launch failure,
-// never as a hung GPU.
-__device__ __forceinline__ void prog_wait(const int* cnt, int target) {
+// Watchdog for every spin in this kernel: a lost completion must never hang the GPU.  The first wait that exceeds
+// the limit records {code, op, CTA, 1} in g_prog_abort and every spin loop bails out once that is set: the kernel
+// terminates (with garbage results) and the host reads the record with b200awq_debug_read under knob 3 = 3.
+// [0..3] = first record; [4 + cta * 10 + warp] = (code << 16 | op) of the wait each warp abandoned (0 = none)
+__device__ int g_prog_abort[4 + 256 * 10];
+cudaError_t program_abort_read(void* dst, size_t bytes) {
+  return cudaMemcpyFromSymbol(dst, g_prog_abort, bytes < sizeof(g_prog_abort) ? bytes : sizeof(g_prog_abort));
+}
+cudaError_t program_abort_clear(cudaStream_t st) {
+  void* p = nullptr;
+  cudaError_t e = cudaGetSymbolAddress(&p, g_prog_abort);
+  return e != cudaSuccess ? e : cudaMemsetAsync(p, 0, sizeof(g_prog_abort), st);
+}
+struct ProgWatch {
   unsigned long long t_start = 0;
   int spins = 0;
-  while (ld_acquire_s32(cnt) < target) {
-    if ((++spins & 1023) == 0) {
+  // returns true when the caller must give up
+  __device__ __forceinline__ bool tick(int code, int op) {
+    if ((++spins & 255) == 0) {
+      if (*reinterpret_cast<volatile int*>(&g_prog_abort[3]) != 0) {
+        if (blockIdx.x < 256 && g_prog_abort[4 + blockIdx.x * 10 + (threadIdx.x >> 5)] == 0)
+          g_prog_abort[4 + blockIdx.x * 10 + (threadIdx.x >> 5)] = (code << 16) | (op & 0xffff);
+        return true;
+      }
       const unsigned long long now = prog_timer();
       if (t_start == 0) t_start = now;
-      else if (now - t_start > 2000000000ull) __trap();
+      else if (now - t_start > 500000000ull) {
+        if (atomicCAS(&g_prog_abort[3], 0, 1) == 0) {
+          g_prog_abort[0] = code;
+          g_prog_abort[1] = op;
+          g_prog_abort[2] = blockIdx.x;
+        }
+        if (blockIdx.x < 256 && g_prog_abort[4 + blockIdx.x * 10 + (threadIdx.x >> 5)] == 0)
+          g_prog_abort[4 + blockIdx.x * 10 + (threadIdx.x >> 5)] = (code << 16) | (op & 0xffff);
+        return true;
+      }
     }
+    return false;
+  }
+};
+enum { kWStaged = 1, kWExtDep = 2, kWEmpty = 3, kWFull = 4, kWGate = 5, kWRedOk = 6, kWStagedOp = 7, kWDutyY = 8,
+       kWDutySilu = 9, kWCopy = 10, kWSilu = 11, kWNorm = 12 };
+__device__ __forceinline__ void prog_wait(const int* cnt, int target, int code, int op) {
+  ProgWatch wd;
+  while (ld_acquire_s32(cnt) < target)
+    if (wd.tick(code, op)) break;
+}
+// returns false when the wait was abandoned (abort): the caller must not touch the barrier's stage any more
+__device__ __forceinline__ bool prog_mbar_wait(uint64_t* bar, uint32_t parity, int code, int op) {
+  ProgWatch wd;
+  while (!mbar_try_wait(bar, parity))
+    if (wd.tick(code, op)) return false;
+  return true;
+}
+__device__ __forceinline__ void prog_wait_smem(volatile int* flag, int target, int code, int op) {
+  ProgWatch wd;
+  while (*flag < target)
+    if (wd.tick(code, op)) break;
+}
+
+// "Row op % 4 is clean": normally read from the shared-memory flag the duty warp keeps ahead; if the flag lags (the
+// duty warp only refreshes it between its own waits) the waiting thread checks the global counter itself - a lost
+// wake-up here deadlocked the Llama-3-8B shapes.
+__device__ __forceinline__ void prog_wait_row_clean(volatile int* red_ok, const int* zeroed, int op, int nblk) {
+  ProgWatch wd;
+  while (*red_ok < op) {
+    if (op < 4 || ld_acquire_s32(&zeroed[op - 4]) >= nblk) break;
+    if (wd.tick(kWRedOk, op)) break;
   }
 }
 
-// mbarrier wait with the same watchdog (a TMA load that never completes must not hang the GPU)
-__device__ __forceinline__ void prog_mbar_wait(uint64_t* bar, uint32_t parity) {
-  unsigned long long t_start = 0;
-  int spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 4095) == 0) {
-      const unsigned long long now = prog_timer();
-      if (t_start == 0) t_start = now;
-      else if (now - t_start > 2000000000ull) __trap();
-    }
-  }
-}
+constexpr int kProgThreads = kV3Threads + 32;   // producer warp + 8 consumer warps + duty warp
 
+// Reclamation of the accumulator rows (off the critical path, run by the duty warp of every CTA):
+//   op i adds into row i % 4; its sums are read while op i+1 stages its activations.
+//   staged[i]  counts CTAs whose consumers finished staging op i (= finished reading row i-1);
+//   zeroed[j]  counts CTAs whose duty warp stored its slice of op j's fp16 output and zeroed its slice of row j.
+//   Duty warp, iteration i = 1..n_ops: make sure row i % 4 is clean for this CTA's REDs of op i (zeroed[i-4]),
+//   wait for its slice of row i-1, store y[i-1] (and the SiLU*mul output of op i), publish staged[i] for the CTA,
+//   wait until every CTA has staged op i, zero its slice of row i-1, publish zeroed[i-1].
 template <int SPW>
-__global__ void __launch_bounds__(kV3Threads, 1)
-    program_kernel(const ProgOp* __restrict__ ops, int n_ops, float* __restrict__ acc3, int acc_stride,
-                   int* __restrict__ done, int M, int dbg, int gate) {
+__global__ void __launch_bounds__(kProgThreads, 1)
+    program_kernel(const ProgOp* __restrict__ ops, int n_ops, unsigned long long* __restrict__ rows, int acc_stride,
+                   int* __restrict__ staged, int* __restrict__ zeroed, int M, int dbg, int gate) {
   constexpr int MT = kProgMT, NS = kV3Warps * SPW;
   extern __shared__ __align__(1024) uint8_t pg_smem[];
   uint8_t* ring = pg_smem;
@@ -148,9 +241,12 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   uint64_t* full = reinterpret_cast<uint64_t*>(colacc + kV3Warps * MT * kV3TileCols);
   uint64_t* empty = full + NS;
   int* flags = reinterpret_cast<int*>(empty + NS);
-  int* warp_cb = flags + 16;
+  int* warp_cb = flags;                 // [8] column block of each warp's pending sums
+  int* warp_ntl = flags + 8;            // [8] tiles those sums cover
+  volatile int* pub_op = reinterpret_cast<volatile int*>(flags + 16);     // ops whose sums this CTA has pushed
+  volatile int* red_ok = reinterpret_cast<volatile int*>(flags + 17);     // highest op whose row is clean for REDs
+  volatile int* staged_op = reinterpret_cast<volatile int*>(flags + 18);  // ops this CTA's consumers have staged
   float* wsum = reinterpret_cast<float*>(flags + 32);  // 8 floats (+ pad)
-  volatile int* pub_op = reinterpret_cast<volatile int*>(flags + 24);  // ops this CTA has published so far
   __half* xs = reinterpret_cast<__half*>(pg_smem + prog_fixed_smem(SPW));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -164,9 +260,18 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     }
     fence_mbar_init();
     *pub_op = 0;
+    *red_ok = 0;
+    *staged_op = 0;
   }
-  for (int i = tid; i < kV3Warps * MT * kV3TileCols; i += kV3Threads) colacc[i] = 0.f;
+  for (int i = tid; i < kV3Warps * MT * kV3TileCols; i += kProgThreads) colacc[i] = 0.f;
   __syncthreads();
+
+  // this CTA's share of an n-element row, in units of 8 elements
+  auto slice8 = [&](int n, int& lo, int& hi) {
+    const int u = n >> 3;
+    lo = (int)((int64_t)u * bid / nblk) << 3;
+    hi = (int)((int64_t)u * (bid + 1) / nblk) << 3;
+  };
 
   if (warp == 0) {
     // ============================================================ producer: the weight stream of ALL ops
@@ -189,22 +294,13 @@ __global__ void __launch_bounds__(kV3Threads, 1)
         const int a = t0 + (int)((int64_t)ntile * w / kV3Warps);
         const int bnd = t0 + (int)((int64_t)ntile * (w + 1) / kV3Warps);
         int cb = a / TPC, kt = a - cb * TPC;
-        // gate (knob 10): this SM's REDs / release of op-1 queue behind its own outstanding bulk loads; hold the
-        // next op's loads back until they are on their way (the ring refills during the wait + staging that follow)
-        if (gate && op > 0) {
-          int spins = 0;
-          unsigned long long t_start = 0;
-          while (*pub_op < op) {
-            if ((++spins & 4095) == 0) {
-              const unsigned long long now = prog_timer();
-              if (t_start == 0) t_start = now;
-              else if (now - t_start > 2000000000ull) __trap();
-            }
-          }
-        }
+        // gate (knob 10): hold the next op's loads back until this CTA's sums of the previous op are on their way
+        // (measured +9 %: the REDs do not queue behind a fresh burst of bulk loads; the ring refills while the
+        // consumers poll and stage)
+        if (gate && op > 0) prog_wait_smem(pub_op, op, kWGate, op);
         for (int t = a; t < bnd; ++t) {
           const int stage = w * SPW + stage_i;
-          prog_mbar_wait(&empty[stage], ph ^ 1);
+          if (!prog_mbar_wait(&empty[stage], ph ^ 1, kWEmpty, op)) return;
           const int grp_abs = (kt * kV3TileRows) >> g_shift;
           uint8_t* st = ring + (size_t)stage * kV3TileBytes;
           uint8_t* sa = aux + (size_t)stage * kV3AuxBytes;
@@ -221,6 +317,101 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     return;
   }
 
+  if (warp == kV3Warps + 1) {
+    // ============================================================ duty warp: outputs + row reclamation
+    // red_ok runs ahead of the reclamation: op j may add into row j % 4 as soon as every CTA has zeroed its slice
+    // after op j-4 (zeroed[j-4] complete); checked without blocking at every step so the consumers never wait for it
+    int rk = 0;
+    auto advance_red_ok = [&]() {
+      if (lane == 0) {
+        int r = rk;
+        while (r + 1 < n_ops && (r + 1 < kProgRows || ld_acquire_s32(&zeroed[r + 1 - kProgRows]) >= nblk)) ++r;
+        if (r != rk)
+          asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(const_cast<int*>(red_ok))), "r"(r) : "memory");
+        rk = r;
+      }
+    };
+    for (int i = 1; i <= n_ops; ++i) {
+      const ProgOp* po = ops + i - 1;
+      unsigned long long* R_prev = rows + (size_t)((i - 1) % kProgRows) * acc_stride;
+      advance_red_ok();
+      // ---- this CTA's slice of op i-1's fp16 output (polls until the slice is complete)
+      const int TPCp = po->K / kV3TileRows;
+      int ylo, yhi;
+      slice8(po->N, ylo, yhi);
+      for (int c = ylo + lane * 8; c < yhi; c += 32 * 8) {
+        uint4 v;
+        ProgWatch wd;
+        while (!prog_prev8(R_prev, po->bias, c, TPCp, v))
+          if (wd.tick(kWDutyY, i)) break;
+        *reinterpret_cast<uint4*>(po->y + c) = v;
+      }
+      if (i < n_ops) {
+        const ProgOp* o = ops + i;
+        // ---- this CTA's slice of the SiLU*mul output op i's prologue stands for
+        if (o->prologue == kProSilu && o->xout != nullptr) {
+          const bool from_prev = o->src_prev != 0;
+          const unsigned long long* pr = R_prev + o->src_off;
+          const __half* pbias = (from_prev && po->bias != nullptr) ? po->bias + o->src_off : nullptr;
+          const int K = o->K;
+          int xlo, xhi;
+          slice8(K, xlo, xhi);
+          for (int c = xlo + lane * 8; c < xhi; c += 32 * 8) {
+            uint4 gv, uv;
+            if (from_prev) {
+              ProgWatch wd;
+              while (!prog_prev8(pr, pbias, c, TPCp, gv))
+                if (wd.tick(kWDutySilu, i)) break;
+              while (!prog_prev8(pr, pbias, K + c, TPCp, uv))
+                if (wd.tick(kWDutySilu, i)) break;
+            } else {
+              gv = ldcg_u4(o->src + c);
+              uv = ldcg_u4(o->src + K + c);
+            }
+            const __half* gh = reinterpret_cast<const __half*>(&gv);
+            const __half* uh = reinterpret_cast<const __half*>(&uv);
+            uint4 ov;
+            __half* oh = reinterpret_cast<__half*>(&ov);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float gf = __half2float(gh[j]), uf = __half2float(uh[j]);
+              oh[j] = __float2half_rn(gf / (1.f + __expf(-gf)) * uf);
+            }
+            *reinterpret_cast<uint4*>(o->xout + c) = ov;
+          }
+        }
+        // ---- publish "this CTA has staged op i", wait for everybody, recycle row i-1
+        __syncwarp();   // EVERY lane is done polling row i-1 (lane 0 alone publishing let other CTAs zero the row
+                        // under this warp's slower lanes: they then polled zeros for ever)
+        if (lane == 0) {
+          ProgWatch wd;
+          int sv;
+          do {
+            asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(sv) : "r"(smem_u32(const_cast<int*>(staged_op))) : "memory");
+            if (wd.tick(kWStagedOp, i)) break;
+          } while (sv < i);
+          red_release_add_s32(&staged[i], 1);
+        }
+        advance_red_ok();
+        if (lane == 0) prog_wait(&staged[i], nblk, kWStaged, i);
+        __syncwarp();
+        int zlo, zhi;
+        slice8(acc_stride, zlo, zhi);
+        for (int c = zlo + lane * 2; c < zhi && dbg != 4; c += 32 * 2)   // (knob 3 = 4 keeps the rows for inspection)
+          *reinterpret_cast<ulonglong2*>(R_prev + c) = make_ulonglong2(0ull, 0ull);
+        __syncwarp();
+        if (lane == 0) red_release_add_s32(&zeroed[i - 1], 1);
+      } else {
+        // epilogue: every CTA read only its own slice of the last row - zero exactly that slice (columns >= N are
+        // never written); all rows are zero again when the kernel exits
+        __syncwarp();
+        for (int c = ylo + lane * 2; c < yhi && dbg != 4; c += 32 * 2)
+          *reinterpret_cast<ulonglong2*>(R_prev + c) = make_ulonglong2(0ull, 0ull);
+      }
+    }
+    return;
+  }
+
   // ================================================================ consumers
   const int cw = warp - 1;
   const int ct = tid - 32;
@@ -229,46 +420,27 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   float* my_red = red + (size_t)cw * MT * kGvRedStride;
   float* my_col = colacc + (size_t)cw * MT * kV3TileCols;
   constexpr int NCT = kV3Warps * 32;
-  // this CTA's share of an n-element row, in units of 8 elements
-  auto slice8 = [&](int n, int& lo, int& hi) {
-    const int u = n >> 3;
-    lo = (int)((int64_t)u * bid / nblk) << 3;
-    hi = (int)((int64_t)u * (bid + 1) / nblk) << 3;
+
+  // add `cols` [256] (shared memory, summed over nsrc sources src_stride floats apart) covering ntl tiles into
+  // column block cb of the op's packed row
+  auto push_cols = [&](float* cols, int nsrc, int src_stride, int cb, int ntl, int t, int nthreads,
+                       unsigned long long* R_cur) {
+    for (int c = t; c < kV3TileCols; c += nthreads) {
+      float v = 0.f;
+      for (int sidx = 0; sidx < nsrc; ++sidx) {
+        v += cols[sidx * src_stride + c];
+        cols[sidx * src_stride + c] = 0.f;
+      }
+      red_add_u64(R_cur + cb * kV3TileCols + c, prog_pack(v, ntl));
+    }
   };
 
   int stage_i = 0;
   uint32_t ph = 0;
-  for (int op = 0; op <= n_ops; ++op) {
-    // op == n_ops: the epilogue pass - publish the last op's output, leave the accumulators zero
-    const bool tail = op == n_ops;
-    const ProgOp* o = ops + (tail ? n_ops - 1 : op);
-    float* A_cur = acc3 + (size_t)(op % 3) * acc_stride;          // this op's split-K sums
-    float* A_prev = acc3 + (size_t)((op + 2) % 3) * acc_stride;   // the previous op's (complete after the wait)
-    float* A_free = acc3 + (size_t)((op + 1) % 3) * acc_stride;   // read one op ago by everybody: zero it now
-
-    PROG_STAMP(0);
-    // ---- (1) every CTA has added its partial sums of the previous op
-    if (op > 0) {
-      if (ct == 0) prog_wait(&done[op - 1], nblk);
-      named_bar_sync_gv(1, NCT);
-    }
-    PROG_STAMP(1);
-
-    // ---- epilogue pass: store the last op's fp16 output, leave all accumulator rows zero
-    if (tail) {
-      const ProgOp* po = ops + op - 1;
-      int ylo, yhi, zlo, zhi;
-      slice8(po->N, ylo, yhi);
-      for (int c = ylo + ct * 8; c < yhi; c += NCT * 8)
-        *reinterpret_cast<uint4*>(po->y + c) = prog_prev8(A_prev, po->bias, c);
-      slice8(acc_stride, zlo, zhi);
-      for (int c = zlo + ct * 4; c < zhi; c += NCT * 4) *reinterpret_cast<float4*>(A_free + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      // every CTA reads only its own slice of the last row: zero exactly that slice (columns >= N are never written)
-      named_bar_sync_gv(1, NCT);
-      for (int c = ylo + ct * 4; c < yhi; c += NCT * 4) *reinterpret_cast<float4*>(A_prev + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      break;
-    }
-
+  for (int op = 0; op < n_ops; ++op) {
+    const ProgOp* o = ops + op;
+    unsigned long long* R_cur = rows + (size_t)(op % kProgRows) * acc_stride;
+    const unsigned long long* R_prev = rows + (size_t)((op + kProgRows - 1) % kProgRows) * acc_stride;
     const int K = o->K, N = o->N, G = o->G, g_shift = o->g_shift;
     const int TPC = K / kV3TileRows;
     const int T = (N / kV3TileCols) * TPC;
@@ -278,13 +450,27 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     const int a_w = t0 + (int)((int64_t)ntile * cw / kV3Warps);
     const int b_w = t0 + (int)((int64_t)ntile * (cw + 1) / kV3Warps);
 
-    // ---- (2b) stage (and transform) the activations this CTA's tiles need; arithmetic mirrors aux.cu exactly
+    PROG_STAMP(0);
+    // an external source written by an older op of this program: its duty-warp stores must all be visible
+    if (o->ext_dep >= 0) {
+      if (ct == 0) prog_wait(&zeroed[o->ext_dep], nblk, kWExtDep, op);
+      named_bar_sync_gv(1, NCT);
+    }
+    PROG_STAMP(1);
+
+    // ---- stage (and transform) the activations this CTA's tiles need; arithmetic mirrors aux.cu exactly.  A source
+    // inside the previous op's output is polled from its packed row until every needed column is complete.
     {
       const bool from_prev = o->src_prev != 0;
-      const float* pa = A_prev + o->src_off;
+      const unsigned long long* pr = R_prev + o->src_off;
       const __half* pbias = (from_prev && ops[op - 1].bias != nullptr) ? ops[op - 1].bias + o->src_off : nullptr;
+      const int TPCp = from_prev ? ops[op - 1].K / kV3TileRows : 0;
       const __half* src = o->src;
-      auto load8 = [&](int c) -> uint4 { return from_prev ? prog_prev8(pa, pbias, c) : ldcg_u4(src + c); };
+      auto load8 = [&](int c, uint4& v) -> bool {
+        if (from_prev) return prog_prev8(pr, pbias, c, TPCp, v);
+        v = ldcg_u4(src + c);
+        return true;
+      };
       __half* xout = o->xout;
       int xlo = 0, xhi = 0;
       if (xout != nullptr) slice8(K, xlo, xhi);
@@ -296,11 +482,23 @@ __global__ void __launch_bounds__(kV3Threads, 1)
         for (int i = ct * 8; i < k_len; i += NCT * 8) {
           int k = k_start + i;
           if (k >= K) k -= K;
-          *reinterpret_cast<uint4*>(xs + k) = load8(k);
+          uint4 v;
+          ProgWatch wd;
+          while (!load8(k, v))
+            if (wd.tick(kWCopy, op)) break;
+          *reinterpret_cast<uint4*>(xs + k) = v;
         }
       } else if (pro == kProSilu) {
-        auto silu8 = [&](int k) -> uint4 {
-          const uint4 gv = load8(k), uv = load8(K + k);
+        for (int i = ct * 8; i < k_len; i += NCT * 8) {
+          int k = k_start + i;
+          if (k >= K) k -= K;
+          uint4 gv, uv;
+          ProgWatch wd;
+          for (;;) {
+            const bool okg = load8(k, gv), oku = load8(K + k, uv);
+            if (okg && oku) break;
+            if (wd.tick(kWSilu, op)) break;
+          }
           const __half* gh = reinterpret_cast<const __half*>(&gv);
           const __half* uh = reinterpret_cast<const __half*>(&uv);
           uint4 ov;
@@ -310,25 +508,26 @@ __global__ void __launch_bounds__(kV3Threads, 1)
             const float gf = __half2float(gh[j]), uf = __half2float(uh[j]);
             oh[j] = __float2half_rn(gf / (1.f + __expf(-gf)) * uf);
           }
-          return ov;
-        };
-        for (int i = ct * 8; i < k_len; i += NCT * 8) {
-          int k = k_start + i;
-          if (k >= K) k -= K;
-          *reinterpret_cast<uint4*>(xs + k) = silu8(k);
+          *reinterpret_cast<uint4*>(xs + k) = ov;
         }
       } else {
-        // all of the row's loads in flight before the first use (one L2 round trip, not one per chunk pair)
+        // RMSNorm: the whole row.  Both chunks of a thread (and their norm weights) are in flight together.
         float ss = 0.f;
         uint4 nwa = make_uint4(0u, 0u, 0u, 0u), nwb = nwa;
         for (int i = ct * 8; i < K; i += NCT * 16) {
           const int i2 = i + NCT * 8;
           const bool two = i2 < K;
-          const uint4 va = load8(i);
-          const uint4 vb = two ? load8(i2) : make_uint4(0u, 0u, 0u, 0u);
-          if (i < NCT * 16) {   // first pair of chunks: fetch their norm weights in the same round trip
+          uint4 va, vb = make_uint4(0u, 0u, 0u, 0u);
+          if (i < NCT * 16) {
             nwa = __ldg(reinterpret_cast<const uint4*>(o->norm_w + i));
             if (two) nwb = __ldg(reinterpret_cast<const uint4*>(o->norm_w + i2));
+          }
+          ProgWatch wd;
+          for (;;) {
+            const bool oka = load8(i, va);
+            const bool okb = two ? load8(i2, vb) : true;
+            if (oka && okb) break;
+            if (wd.tick(kWNorm, op)) break;
           }
           const __half2* ha = reinterpret_cast<const __half2*>(&va);
           const __half2* hb = reinterpret_cast<const __half2*>(&vb);
@@ -367,41 +566,13 @@ __global__ void __launch_bounds__(kV3Threads, 1)
         }
       }
       named_bar_sync_gv(1, NCT);
-
-      // ---- slice duties, off the critical path: the last consumer warp alone stores this CTA's slice of the
-      // previous op's fp16 output and of the SiLU*mul output, and recycles the accumulator row two ops back,
-      // while the other warps start on their tiles (ordered before this CTA's publish by the barriers of (4))
-      if (cw == kV3Warps - 1) {
-        if (op > 0) {
-          const ProgOp* po = ops + op - 1;
-          int ylo, yhi, zlo, zhi;
-          slice8(po->N, ylo, yhi);
-          for (int c = ylo + lane * 8; c < yhi; c += 32 * 8)
-            *reinterpret_cast<uint4*>(po->y + c) = prog_prev8(A_prev, po->bias, c);
-          slice8(acc_stride, zlo, zhi);
-          for (int c = zlo + lane * 4; c < zhi; c += 32 * 4)
-            *reinterpret_cast<float4*>(A_free + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (pro == kProSilu && xout != nullptr) {
-          for (int c = xlo + lane * 8; c < xhi; c += 32 * 8) {
-            const uint4 gv = load8(c), uv = load8(K + c);
-            const __half* gh = reinterpret_cast<const __half*>(&gv);
-            const __half* uh = reinterpret_cast<const __half*>(&uv);
-            uint4 ov;
-            __half* oh = reinterpret_cast<__half*>(&ov);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float gf = __half2float(gh[j]), uf = __half2float(uh[j]);
-              oh[j] = __float2half_rn(gf / (1.f + __expf(-gf)) * uf);
-            }
-            *reinterpret_cast<uint4*>(xout + c) = ov;
-          }
-        }
-      }
+      // this CTA is done reading the previous op's row: tell the duty warp (it publishes staged[op])
+      if (ct == 0)
+        asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(const_cast<int*>(staged_op))), "r"(op) : "memory");
     }
     PROG_STAMP(2);
 
-    // ---- (3) the persistent-GEMV tile loop over this warp's run of tiles
+    // ---- the persistent-GEMV tile loop over this warp's run of tiles
     auto load_x = [&](int t, int ktile, uint32_t (&xb)[4][2]) {
 #pragma unroll
       for (int bb = 0; bb < 4; ++bb) xb[bb][0] = xb[bb][1] = 0u;
@@ -435,16 +606,17 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       const int stage = cw * SPW + stage_i;
       if (cb != cur_cb) {
         if (cur_cb >= 0 && ntl > 0) {
-          // this warp's run crosses a column block: add its pending sums alone (rare)
+          // this warp's run crosses a column block: push its pending sums alone (rare)
           __syncwarp();
-          v3_add_cols<MT, 32>(my_col, 1, 0, cur_cb, lane, A_cur, M, N);
+          if (op > 0) prog_wait_row_clean(red_ok, zeroed, op, nblk);
+          push_cols(my_col, 1, 0, cur_cb, ntl, lane, 32, R_cur);
         }
         cur_cb = cb;
         ntl = 0;
       }
       ++ntl;
       load_x(t + 1, (kt + 1 == TPC) ? 0 : kt + 1, xnext);
-      prog_mbar_wait(&full[stage], ph);
+      prog_mbar_wait(&full[stage], ph, kWFull, op);
       if (t == a_w) PROG_STAMP(3);
       const uint8_t* st = ring + (size_t)stage * kV3TileBytes;
       const uint8_t* sa = aux + (size_t)stage * kV3AuxBytes;
@@ -465,30 +637,30 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       if (++stage_i == SPW) { stage_i = 0; ph ^= 1; }
     }
 
-    // ---- (4) CTA-level reduction of the per-warp column sums into this op's accumulator row, then publish:
-    // no tickets, no finalisation - the consumers of the next op read the fp32 sums themselves
+    // ---- CTA-level reduction of the per-warp column sums, one packed RED per column; nothing to publish
     PROG_STAMP(4);
-    if (lane == 0) warp_cb[cw] = (ntl > 0) ? cur_cb : -1;
+    if (lane == 0) {
+      warp_cb[cw] = (ntl > 0) ? cur_cb : -1;
+      warp_ntl[cw] = ntl;
+    }
+    if (op > 0 && ct == 0) prog_wait_row_clean(red_ok, zeroed, op, nblk);   // the op's row is clean (duty warp, long since)
     named_bar_sync_gv(1, NCT);
     PROG_STAMP(5);
     {
       int w0 = 0;
       while (w0 < kV3Warps) {
         const int cbg = warp_cb[w0];
-        int w1 = w0 + 1;
-        while (w1 < kV3Warps && warp_cb[w1] == cbg) ++w1;
-        if (cbg >= 0)
-          v3_add_cols<MT, NCT>(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cbg, ct, A_cur, M, N);
+        int w1 = w0 + 1, tiles = warp_ntl[w0];
+        while (w1 < kV3Warps && warp_cb[w1] == cbg) tiles += warp_ntl[w1++];
+        if (cbg >= 0) push_cols(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cbg, tiles, ct, NCT, R_cur);
         w0 = w1;
       }
     }
-    named_bar_sync_gv(1, NCT);
     PROG_STAMP(6);
-    if (ct == 0) {
-      red_release_add_s32(&done[op], 1);
-      *pub_op = op + 1;
-    }
+    if (ct == 0) *pub_op = op + 1;
     PROG_STAMP(7);
+    // (the next op's staging barrier separates these shared-memory reads from the next fold's writes; the last op's
+    // sums are stored by the duty warps)
   }
 }
 
@@ -579,8 +751,10 @@ int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* c
                op.bias, op.y, op.M, op.K, op.N, op.group_size};
     if (M != 1 || !gemv_v3_supported(a)) return B200AWQ_EUNSUPPORTED;
     if ((op.N / kV3TileCols) * (op.K / kV3TileRows) < grid) return B200AWQ_EUNSUPPORTED;  // every CTA owns tiles
+    if (op.K / kV3TileRows >= 256) return B200AWQ_EUNSUPPORTED;   // tile count per column must fit the packed word
     ProgOp p;
     std::memset(&p, 0, sizeof(p));
+    p.ext_dep = -1;
     cudaError_t e = make_tmap_2d(a.qweight, /*int32*/ 1, (uint64_t)(a.N / 8), (uint64_t)a.K, (uint64_t)(a.N / 8) * 4, 32,
                                  kV3TileRows, &p.tmw);
     if (e != cudaSuccess) {
@@ -630,6 +804,13 @@ int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* c
         p.src_off = static_cast<int>((s0 - y0) / 2);
       } else if (overlaps(pv.y, (size_t)pv.N * 2, p.src, src_bytes)) {
         return B200AWQ_EUNSUPPORTED;
+      } else {
+        // a source written by an older op of this program: wait for that op's duty-warp stores
+        for (int j = static_cast<int>(table.size()) - 2; j >= 0; --j)
+          if (overlaps(table[j].y, (size_t)table[j].N * 2, p.src, src_bytes)) {
+            p.ext_dep = j;
+            break;
+          }
       }
       if (p.xout != nullptr && overlaps(p.xout, (size_t)op.K * 2, pv.y, (size_t)pv.N * 2)) return B200AWQ_EUNSUPPORTED;
     }
@@ -659,7 +840,7 @@ int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* c
   pr->xs_bytes = (size_t)(max_K + 8) * 2 * kProgMT;
   cudaError_t e = cudaGetDevice(&pr->device);
   if (e == cudaSuccess) e = cudaMalloc(&pr->d_ops, table.size() * sizeof(ProgOp));
-  if (e == cudaSuccess) e = cudaMalloc(&pr->d_done, (table.size() + 1) * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&pr->d_done, 2 * (table.size() + 1) * sizeof(int));
   if (e == cudaSuccess) e = cudaMemcpy(pr->d_ops, table.data(), table.size() * sizeof(ProgOp), cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(program_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
@@ -681,11 +862,14 @@ int program_m(const Program* p) { return p->M; }
 int program_num_ops(const Program* p) { return p->n_ops; }
 
 cudaError_t program_run(Program* p, float* acc_ws, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(p->d_done, 0, (size_t)(p->n_ops + 1) * sizeof(int), st);
+  // staged[] and zeroed[] counters (see program_kernel)
+  cudaError_t e = program_abort_clear(st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(p->d_done, 0, (size_t)2 * (p->n_ops + 1) * sizeof(int), st);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(prog_sm_count());
-  cfg.blockDim = dim3(kV3Threads);
+  cfg.blockDim = dim3(kProgThreads);
   const int spw = knob(9) == 1 ? 1 : 2;
   cfg.dynamicSmemBytes = prog_fixed_smem(spw) + p->xs_bytes;
   cfg.stream = st;
@@ -695,10 +879,13 @@ cudaError_t program_run(Program* p, float* acc_ws, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const ProgOp* ops = p->d_ops;
-  const int dbg = knob(3) == 2 ? 1 : 0, gate = knob(10) == 2 ? 0 : 1;   // gate on unless knob 10 == 2
+  const int dbg = knob(3), gate = knob(10) == 2 ? 0 : 1;   // gate on unless knob 10 == 2
+  unsigned long long* rows = reinterpret_cast<unsigned long long*>(acc_ws);
+  int* staged = p->d_done;
+  int* zeroed = p->d_done + (p->n_ops + 1);
   if (spw == 1)
-    return cudaLaunchKernelEx(&cfg, program_kernel<1>, ops, p->n_ops, acc_ws, p->acc_stride, p->d_done, p->M, dbg, gate);
-  return cudaLaunchKernelEx(&cfg, program_kernel<2>, ops, p->n_ops, acc_ws, p->acc_stride, p->d_done, p->M, dbg, gate);
+    return cudaLaunchKernelEx(&cfg, program_kernel<1>, ops, p->n_ops, rows, p->acc_stride, staged, zeroed, p->M, dbg, gate);
+  return cudaLaunchKernelEx(&cfg, program_kernel<2>, ops, p->n_ops, rows, p->acc_stride, staged, zeroed, p->M, dbg, gate);
 }
 
 void program_destroy(Program* p) {

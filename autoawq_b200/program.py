@@ -143,7 +143,7 @@ class DecodeProgram:
         if self._handle is not None:
             with ext._DeviceGuard(dev):
                 st = ext._stream(dev)
-                ws = ext._workspace(dev, st, lib.b200awq_workspace_bytes(3, 0, (self._max_n + 7) & ~7))
+                ws = ext._workspace(dev, st, lib.b200awq_workspace_bytes(8, 0, (self._max_n + 7) & ~7))
                 code = lib.b200awq_program_run(self._handle, ws.data_ptr(), ws.numel(), st)
             check(code, "b200awq_program_run")
             return
@@ -154,6 +154,21 @@ class DecodeProgram:
                 ext.silu_and_mul(o["out"], o["gate_up"])
             else:
                 ext.linear_forward("gemm", o["x"], o["qweight"], o["scales"], o["qzeros"], o["G"], o["bias"], out=o["y"])
+
+    @staticmethod
+    def abort_record():
+        """(code, op, cta, aborted) of the last fused run on this device: the kernel's spin loops give up after 0.5 s
+        instead of hanging the GPU and record which wait failed (csrc/program.cu).  Synchronises the device."""
+        import numpy as np
+
+        prev = lib.b200awq_get_knob(3)
+        lib.b200awq_set_knob(3, 3)
+        buf = np.zeros(4, dtype=np.int32)
+        try:
+            check(lib.b200awq_debug_read(buf.ctypes.data_as(ctypes.c_void_p), buf.nbytes), "b200awq_debug_read")
+        finally:
+            lib.b200awq_set_knob(3, prev)
+        return tuple(int(v) for v in buf)
 
     def close(self) -> None:
         if self._handle is not None:

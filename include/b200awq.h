@@ -147,8 +147,8 @@ typedef struct b200awq_program* b200awq_program_t;
 int b200awq_program_create(const b200awq_op_t* ops, int n_ops, b200awq_program_t* out);
 /* number of fused kernel ops (= linear ops) of the program; 0 for a null handle */
 int b200awq_program_num_ops(b200awq_program_t prog);
-/* workspace: b200awq_workspace_bytes(3, K, max N over the program's linears rounded up to 8): three fp32
- * accumulator rows; zero-initialised and left all-zero like the per-op workspace (the same buffer may serve both) */
+/* workspace: b200awq_workspace_bytes(8, K, max N over the program's linears rounded up to 8): four rows of 64-bit
+ * packed split-K sums; zero-initialised and left all-zero like the per-op workspace (the same buffer may serve both) */
 int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
 int b200awq_program_destroy(b200awq_program_t prog);
 

@@ -69,7 +69,15 @@ def _record(api, blocks, h, M):
     return bufs
 
 
+def _no_abort(tag=""):
+    from autoawq_b200.program import DecodeProgram
+
+    rec = DecodeProgram.abort_record()
+    assert rec[3] == 0, f"{tag}: program kernel gave up waiting: code={rec[0]} op={rec[1]} cta={rec[2]}"
+
+
 def _check_against_oracle(blocks, bufs, tag):
+    _no_abort(tag)
     for li, (b, t) in enumerate(zip(blocks, bufs)):
         v = {k: x.float().cpu().numpy().astype(np.float16) for k, x in t.items()}
         np.testing.assert_allclose(v["xn"], O.rmsnorm_f64(v["h"], b.norm1, EPS), rtol=2e-3, atol=2e-3,

@@ -51,8 +51,13 @@ nops = prog.kernel_ops
 ext.set_knob(3, 2)
 runs = []
 for it in range(6):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     prog.run()
+    e1.record()
     torch.cuda.synchronize()
+    print(f"run {it}: {e0.elapsed_time(e1) * 1e3:.1f} us, abort record {DecodeProgram.abort_record()}")
+    ext.set_knob(3, 2)
     buf = np.zeros((32, 8, 8), dtype=np.uint64)
     lib.b200awq_debug_read(buf.ctypes.data_as(ctypes.c_void_p), buf.nbytes)
     if it >= 2:
