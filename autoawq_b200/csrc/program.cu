@@ -231,7 +231,7 @@ constexpr int kProgThreads = kV3Threads + 32;   // producer warp + 8 consumer wa
 template <int SPW>
 __global__ void __launch_bounds__(kProgThreads, 1)
     program_kernel(const ProgOp* __restrict__ ops, int n_ops, unsigned long long* __restrict__ rows, int acc_stride,
-                   int* __restrict__ staged, int* __restrict__ zeroed, int M, int dbg, int gate) {
+                   int* __restrict__ staged, int* __restrict__ zeroed, int M, int dbg, int gate, int backoff) {
   constexpr int MT = kProgMT, NS = kV3Warps * SPW;
   extern __shared__ __align__(1024) uint8_t pg_smem[];
   uint8_t* ring = pg_smem;
@@ -342,8 +342,10 @@ __global__ void __launch_bounds__(kProgThreads, 1)
       for (int c = ylo + lane * 8; c < yhi; c += 32 * 8) {
         uint4 v;
         ProgWatch wd;
-        while (!prog_prev8(R_prev, po->bias, c, TPCp, v))
+        while (!prog_prev8(R_prev, po->bias, c, TPCp, v)) {
           if (wd.tick(kWDutyY, i)) break;
+          if (backoff) __nanosleep(400);   // off the critical path: do not hammer the lines the REDs are landing on
+        }
         *reinterpret_cast<uint4*>(po->y + c) = v;
       }
       if (i < n_ops) {
@@ -360,10 +362,14 @@ __global__ void __launch_bounds__(kProgThreads, 1)
             uint4 gv, uv;
             if (from_prev) {
               ProgWatch wd;
-              while (!prog_prev8(pr, pbias, c, TPCp, gv))
+              while (!prog_prev8(pr, pbias, c, TPCp, gv)) {
                 if (wd.tick(kWDutySilu, i)) break;
-              while (!prog_prev8(pr, pbias, K + c, TPCp, uv))
+                if (backoff) __nanosleep(400);
+              }
+              while (!prog_prev8(pr, pbias, K + c, TPCp, uv)) {
                 if (wd.tick(kWDutySilu, i)) break;
+                if (backoff) __nanosleep(400);
+              }
             } else {
               gv = ldcg_u4(o->src + c);
               uv = ldcg_u4(o->src + K + c);
@@ -647,12 +653,15 @@ __global__ void __launch_bounds__(kProgThreads, 1)
     named_bar_sync_gv(1, NCT);
     PROG_STAMP(5);
     {
+      // one push per column block this CTA touched: consecutive warps with the same block, empty warps (-1, their
+      // column sums are zero) in between included
       int w0 = 0;
       while (w0 < kV3Warps) {
         const int cbg = warp_cb[w0];
+        if (cbg < 0) { ++w0; continue; }
         int w1 = w0 + 1, tiles = warp_ntl[w0];
-        while (w1 < kV3Warps && warp_cb[w1] == cbg) tiles += warp_ntl[w1++];
-        if (cbg >= 0) push_cols(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cbg, tiles, ct, NCT, R_cur);
+        while (w1 < kV3Warps && (warp_cb[w1] == cbg || warp_cb[w1] < 0)) tiles += warp_cb[w1] < 0 ? 0 : warp_ntl[w1], ++w1;
+        push_cols(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cbg, tiles, ct, NCT, R_cur);
         w0 = w1;
       }
     }
@@ -883,9 +892,12 @@ cudaError_t program_run(Program* p, float* acc_ws, cudaStream_t st) {
   unsigned long long* rows = reinterpret_cast<unsigned long long*>(acc_ws);
   int* staged = p->d_done;
   int* zeroed = p->d_done + (p->n_ops + 1);
+  const int backoff = knob(11) == 2 ? 0 : 1;   // duty-warp polls sleep 400 ns between attempts unless knob 11 == 2
   if (spw == 1)
-    return cudaLaunchKernelEx(&cfg, program_kernel<1>, ops, p->n_ops, rows, p->acc_stride, staged, zeroed, p->M, dbg, gate);
-  return cudaLaunchKernelEx(&cfg, program_kernel<2>, ops, p->n_ops, rows, p->acc_stride, staged, zeroed, p->M, dbg, gate);
+    return cudaLaunchKernelEx(&cfg, program_kernel<1>, ops, p->n_ops, rows, p->acc_stride, staged, zeroed, p->M, dbg, gate,
+                              backoff);
+  return cudaLaunchKernelEx(&cfg, program_kernel<2>, ops, p->n_ops, rows, p->acc_stride, staged, zeroed, p->M, dbg, gate,
+                            backoff);
 }
 
 void program_destroy(Program* p) {

@@ -368,8 +368,8 @@ def main():
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(ach / peaks["hbm_gbs"], 4),
                 # dram__bytes_read + write per program_kernel launch: profiles/r01_ncu_program_kernel_bench.csv
-                # (3,626.4 MB read + 9-14 MB written; algorithmic 3,626 MB)
-                "traffic": 3638000000 if a.layers == LAYERS else None,
+                # (3,629.7 MB read + 27-29 MB written; algorithmic 3,626 MB)
+                "traffic": 3658000000 if a.layers == LAYERS else None,
                 "kernel": "program_kernel (persistent decode program: 128 linears + glue per launch)",
                 "peak_src": peaks["src"] + " (hbm_gbs)",
                 "per_launch": {"avg_us": round(step_s * 1e6, 2), "alg_bytes": alg_bytes,
