@@ -8,23 +8,22 @@
 // WHOLE op list and keeps its shared-memory ring full across op boundaries: while the consumers of op i reduce,
 // publish and wait for the grid-wide completion of op i, the tiles of op i+1 are already landing.
 //
-// Structure (one CTA per SM, launched cooperatively so that all CTAs are co-resident):
+// Structure (one CTA per SM, launched cooperatively so that all CTAs are co-resident; 10 warps per CTA):
 //   * producer warp: as in the persistent GEMV (gemv.cu) - lane w feeds consumer warp w's private stages with
 //     8 KB weight tiles (TMA 2-D, 128B swizzle) + the tile's group scales / zeros - but over all ops back to back;
 //     the tensor maps live in the device-resident op table;
-//   * consumers, per op: (1) wait until every CTA has added its split-K partial sums of the previous op (acquiring
-//     poll of done[op-1]; one release-add per CTA), (2) build the op's activations in shared memory straight from
-//     the previous op's fp32 accumulator row - fp16(acc + bias) is exactly what the per-op path stores - applying the
-//     recorded glue op on the fly (RMSNorm: every CTA recomputes the row's norm from L2, 16 KB; SiLU*mul: only the
-//     k-range of the CTA's own tiles) with the arithmetic of the stand-alone kernels (aux.cu); (3) the tile loop and
-//     per-group fold of the persistent GEMV, unchanged (gemv_tile.cuh); (4) REDs of the CTA's column sums into the
-//     op's accumulator row, one release-add.  No tickets, no finalisation pass, no fp16 round trip through memory
-//     on the critical path: first version with both measured ~10 us per op boundary
-//     (profiles/r01_program_l2ahead_sweep.md).
-//   * three accumulator rows rotate: op i adds into row i % 3, reads row (i-1) % 3, and each CTA zeroes its slice
-//     of row (i-2) % 3 (everybody finished reading it one op ago).  Every CTA also stores its slice of the previous
-//     op's fp16 output and of the glue op's output, so after a run every tensor of the per-op path holds the same
-//     values; an epilogue pass does that for the last op and leaves all rows zero.
+//   * 8 consumer warps, per op: (1) poll the columns they need of the previous op's PACKED row until complete (each
+//     64-bit word carries the split-K sum and the number of tiles that contributed - see "packed split-K hand-off"
+//     below), (2) build the op's activations in shared memory from it - fp16(sum + bias) is exactly what the
+//     per-op path stores - applying the recorded glue op on the fly (RMSNorm: every CTA recomputes the row's norm
+//     from L2; SiLU*mul: only the k-range of the CTA's own tiles) with the arithmetic of the stand-alone kernels
+//     (aux.cu); (3) the tile loop and per-group fold of the persistent GEMV, unchanged (gemv_tile.cuh); (4) one
+//     packed RED per column of each column block the CTA touched.  Nothing to publish, nothing to acknowledge;
+//   * duty warp: off the critical path, stores this CTA's slice of every op's fp16 output (and of the SiLU*mul
+//     output), so every tensor of the per-op path holds the same values after a run, and recycles the four rotating
+//     rows (staged[] / zeroed[] counters, see program_kernel).
+//   History (profiles/r01_program_l2ahead_sweep.md): tickets + last-arriver finalisation: ~10 us per
+//   op boundary, 529 tok/s; fp32 row + one release/acquire counter per op: ~8 us, 652 tok/s; packed rows: 734-744.
 //
 // Reference call sequence this replaces: awq/modules/fused/block.py:117-170 (norm -> qkv -> ... -> o -> norm ->
 // mlp) with awq/modules/fused/mlp.py:41-55 (gate/up GEMM, silu*mul, down GEMM), each a separate awq_ext call.
