@@ -297,6 +297,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
