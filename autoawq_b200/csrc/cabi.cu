@@ -190,4 +190,40 @@ int b200awq_program_destroy(b200awq_program_t prog) {
   program_destroy(reinterpret_cast<Program*>(prog));
   return B200AWQ_OK;
 }
+
+int b200awq_topk_softmax(const float* gating_output, float* topk_weights, int32_t* topk_ids,
+                         int32_t* token_expert_indices, int M, int E, int topk, b200awq_stream_t stream) {
+  if (M < 0 || E <= 0 || topk <= 0 || topk > E) return B200AWQ_EINVAL;
+  if (M == 0) return B200AWQ_OK;
+  if (!gating_output || !topk_weights || !topk_ids || !token_expert_indices) return B200AWQ_EINVAL;
+  if (E > 4096) return B200AWQ_EUNSUPPORTED;
+  return fold(topk_softmax(gating_output, topk_weights, topk_ids, token_expert_indices, M, E, topk,
+                           static_cast<cudaStream_t>(stream)));
+}
+
+int b200awq_moe_align_block_size(const int32_t* topk_ids, int numel, int num_experts, int block_size,
+                                 int32_t* sorted_ids, int32_t* expert_ids, int32_t* num_tokens_post_pad,
+                                 b200awq_stream_t stream) {
+  if (numel < 0 || num_experts <= 0 || block_size <= 0) return B200AWQ_EINVAL;
+  if (!topk_ids || !sorted_ids || !expert_ids || !num_tokens_post_pad) return B200AWQ_EINVAL;
+  return fold(moe_align_block_size(topk_ids, numel, num_experts, block_size, sorted_ids, expert_ids, num_tokens_post_pad,
+                                   static_cast<cudaStream_t>(stream)));
+}
+
+int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int32_t* qweight, const void* scales,
+                                 const int32_t* qzeros, const float* topk_weights, const int32_t* sorted_ids,
+                                 const int32_t* expert_ids, const int32_t* num_tokens_post_pad, void* y, int T, int topk,
+                                 int sorted_len, int K, int N, int group_size, int mul_weights, int block_size,
+                                 b200awq_stream_t stream) {
+  const int G = group_size <= 0 ? K : group_size;
+  if (T < 0 || topk <= 0 || sorted_len < 0 || !shape_ok(1, K, N, G) || block_size <= 0) return B200AWQ_EINVAL;
+  if (x_rows_per_token != 1 && x_rows_per_token != topk) return B200AWQ_EINVAL;
+  if (T == 0) return B200AWQ_OK;
+  if (!x || !qweight || !scales || !qzeros || !topk_weights || !sorted_ids || !expert_ids || !num_tokens_post_pad || !y)
+    return B200AWQ_EINVAL;
+  if (!moe_grouped_supported(K, N, G) || (block_size % 8) != 0) return B200AWQ_EUNSUPPORTED;
+  return fold(moe_grouped_gemm(x, x_rows_per_token == 1 ? 0 : 1, qweight, scales, qzeros, topk_weights, sorted_ids,
+                               expert_ids, num_tokens_post_pad, y, T * topk, topk, sorted_len, K, N, G, mul_weights,
+                               block_size, static_cast<cudaStream_t>(stream)));
+}
 }  // extern "C"

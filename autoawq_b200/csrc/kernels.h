@@ -87,6 +87,17 @@ void program_destroy(Program* p);
 cudaError_t program_debug_read(void* dst, size_t bytes);
 cudaError_t program_abort_read(void* dst, size_t bytes);
 
+// MoE (moe.cu)
+cudaError_t topk_softmax(const float* gating, float* topk_w, int* topk_ids, int* src_rows, int M, int E, int topk,
+                         cudaStream_t st);
+cudaError_t moe_align_block_size(const int* topk_ids, int numel, int num_experts, int block_size, int* sorted_ids,
+                                 int* expert_ids, int* num_post_pad, cudaStream_t st);
+bool moe_grouped_supported(int K, int N, int G);
+cudaError_t moe_grouped_gemm(const void* x, int x_per_slot, const int32_t* qweight, const void* scales,
+                             const int32_t* qzeros, const float* topk_w, const int* sorted_ids, const int* expert_ids,
+                             const int* num_post_pad, void* y, int n_slots, int topk, int sorted_len, int K, int N, int G,
+                             int mul_weights, int block_size, cudaStream_t st);
+
 cudaError_t rmsnorm(const void* x, const void* w, void* out, int rows, int hidden, float eps, cudaStream_t st);
 cudaError_t silu_and_mul(const void* gate_up, void* out, int rows, int d, cudaStream_t st);
 

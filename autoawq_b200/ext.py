@@ -16,6 +16,7 @@ from ._cabi import B200AwqError, check, lib
 __all__ = [
     "gemm_forward_cuda", "dequantize_weights_cuda", "gemv_forward_cuda", "gemmv2_forward_cuda",
     "gemv_forward_cuda_decode", "gemm_forward_cuda_prefill", "layernorm_forward_cuda", "silu_and_mul",
+    "topk_softmax", "moe_alig_block_size", "grouped_gemm_forward",
     "linear_forward", "set_knob", "get_knob", "B200AwqError",
 ]
 
@@ -186,6 +187,72 @@ def silu_and_mul(out, gate_up):
     with _DeviceGuard(out.device):
         code = lib.b200awq_silu_and_mul(gate_up.data_ptr(), out.data_ptr(), rows, d, _stream(out.device))
     check(code, "b200awq_silu_and_mul")
+
+
+# ------------------------------------------------------------------------------------ MoE (awq_ext surface)
+def topk_softmax(topk_weights, topk_ids, token_expert_indicies, gating_output):
+    """awq_ext.topk_softmax (fused/moe.py:162-167): fills the three output tensors [M, topk] from gating_output
+    [M, E] f32 (softmax over experts, top-k, not renormalised)."""
+    _require_cuda(topk_weights, topk_ids, token_expert_indicies, gating_output)
+    if gating_output.dtype != torch.float32 or topk_weights.dtype != torch.float32 \
+            or topk_ids.dtype != torch.int32 or token_expert_indicies.dtype != torch.int32:
+        raise B200AwqError("b200awq: topk_softmax expects f32 gating / weights and i32 index tensors")
+    g = gating_output if gating_output.is_contiguous() else gating_output.contiguous()
+    for t in (topk_weights, topk_ids, token_expert_indicies):
+        if not t.is_contiguous():
+            raise B200AwqError("b200awq: topk_softmax outputs must be contiguous")
+    M, E = g.shape
+    topk = topk_weights.shape[-1]
+    with _DeviceGuard(g.device):
+        code = lib.b200awq_topk_softmax(g.data_ptr(), topk_weights.data_ptr(), topk_ids.data_ptr(),
+                                        token_expert_indicies.data_ptr(), M, E, topk, _stream(g.device))
+    check(code, f"b200awq_topk_softmax(M={M}, E={E}, topk={topk})")
+
+
+def moe_alig_block_size(topk_ids, num_experts, block_size, sorted_token_ids, expert_ids, num_tokens_post_pad):
+    """awq_ext.moe_alig_block_size (sic; fused/moe.py:131-133): fills sorted_token_ids, expert_ids,
+    num_tokens_post_pad from topk_ids [M, topk] i32."""
+    _require_cuda(topk_ids, sorted_token_ids, expert_ids, num_tokens_post_pad)
+    for t in (topk_ids, sorted_token_ids, expert_ids, num_tokens_post_pad):
+        if t.dtype != torch.int32 or not t.is_contiguous():
+            raise B200AwqError("b200awq: moe_alig_block_size expects contiguous int32 tensors")
+    numel = topk_ids.numel()
+    if sorted_token_ids.numel() < numel + num_experts * (block_size - 1) or expert_ids.numel() < numel + num_experts:
+        raise B200AwqError("b200awq: moe_alig_block_size output tensors are too small")
+    with _DeviceGuard(topk_ids.device):
+        code = lib.b200awq_moe_align_block_size(topk_ids.data_ptr(), numel, int(num_experts), int(block_size),
+                                                sorted_token_ids.data_ptr(), expert_ids.data_ptr(),
+                                                num_tokens_post_pad.data_ptr(), _stream(topk_ids.device))
+    check(code, "b200awq_moe_align_block_size")
+
+
+def grouped_gemm_forward(x, qweight, scales, qzeros, topk_weights, sorted_token_ids, expert_ids,
+                         num_tokens_post_padded, mul_weights, split_k_iters=8):
+    """awq_ext.grouped_gemm_forward (fused/moe.py:60-89): x [T, 1 or topk, K] f16, stacked expert weights
+    qweight [E, K, N/8] / scales [E, K/G, N] / qzeros [E, K/G, N/8] -> [T, topk, N] f16."""
+    _require_cuda(x, qweight, scales, qzeros, topk_weights, sorted_token_ids, expert_ids, num_tokens_post_padded)
+    _check_w(qweight, torch.int32, "qweight")
+    _check_w(scales, torch.float16, "scales")
+    _check_w(qzeros, torch.int32, "qzeros")
+    if x.dim() != 3 or x.dtype != torch.float16:
+        raise B200AwqError("b200awq: grouped_gemm_forward expects x [T, 1 or topk, K] float16")
+    if topk_weights.dtype != torch.float32 or not topk_weights.is_contiguous():
+        raise B200AwqError("b200awq: topk_weights must be contiguous float32")
+    E, K, N = qweight.shape[0], qweight.shape[1], qweight.shape[2] * 8
+    G = K // scales.shape[1]
+    T, topk = topk_weights.shape
+    xc = x if x.is_contiguous() else x.contiguous()
+    if xc.shape[0] != T or xc.shape[1] not in (1, topk) or xc.shape[2] != K:
+        raise B200AwqError(f"b200awq: x {tuple(x.shape)} does not match T={T}, topk={topk}, K={K}")
+    y = torch.empty((T, topk, N), dtype=torch.float16, device=x.device)
+    with _DeviceGuard(x.device):
+        code = lib.b200awq_grouped_gemm_forward(
+            xc.data_ptr(), int(xc.shape[1]), qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(),
+            topk_weights.data_ptr(), sorted_token_ids.data_ptr(), expert_ids.data_ptr(),
+            num_tokens_post_padded.data_ptr(), y.data_ptr(), T, topk, sorted_token_ids.numel(), K, N, G,
+            1 if mul_weights else 0, 16, _stream(x.device))
+    check(code, f"b200awq_grouped_gemm_forward(T={T}, topk={topk}, E={E}, K={K}, N={N}, G={G})")
+    return y
 
 
 # ---------------------------------------------------------------------------- awq_v2_ext surface

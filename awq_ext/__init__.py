@@ -8,6 +8,9 @@ from autoawq_b200.ext import (  # noqa: F401
     gemm_forward_cuda,
     gemmv2_forward_cuda,
     gemv_forward_cuda,
+    grouped_gemm_forward,
     layernorm_forward_cuda,
+    moe_alig_block_size,
     silu_and_mul,
+    topk_softmax,
 )

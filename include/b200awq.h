@@ -84,6 +84,34 @@ int b200awq_rmsnorm(const void* x, const void* weight, void* out, int rows, int 
 /* out[r, j] = silu(gate_up[r, j]) * gate_up[r, d + j], j < d  (fp32 math, fp16 in/out) */
 int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200awq_stream_t stream);
 
+/* ---- MoE (awq/modules/fused/moe.py:45-171; Mixtral: awq/models/mixtral.py:129-158) ------------------------------
+ * b200awq_topk_softmax ............ awq_ext.topk_softmax        moe.py:162-167 (fused_topk)
+ * b200awq_moe_align_block_size .... awq_ext.moe_alig_block_size moe.py:131-133
+ * b200awq_grouped_gemm_forward .... awq_ext.grouped_gemm_forward moe.py:60-89
+ *
+ * topk_softmax: softmax over the E experts (fp32), the topk largest probabilities per token (ties: lower expert),
+ * not renormalised; token_expert_indices[m, k] = k * M + m.
+ * moe_align_block_size: flattened slot indices (token * topk + k) grouped by expert in ascending order, every
+ * expert's run padded with `numel` to a multiple of block_size; expert_ids[b] = expert of block b;
+ * *num_tokens_post_pad = total padded length.  sorted_ids holds numel + E * (block_size - 1) entries, expert_ids
+ * numel + E.
+ * grouped_gemm_forward: y [T * topk, N] f16; for every real slot id in sorted_ids[0 .. *num_tokens_post_pad),
+ * y[id] = x_row(id) . deq(W[expert_ids[pos / block_size]]) (* topk_weights[id] if mul_weights), x_row(id) = x[id /
+ * topk] when x_rows_per_token == 1 (x [T, 1, K]) and x[id] when x_rows_per_token == topk (x [T, topk, K]).
+ * qweight [E, K, N/8], scales [E, K/G, N], qzeros [E, K/G, N/8] (stacked GEMM layout).  block_size is 16 at the
+ * reference's call site (moe.py:54-56) and must be a multiple of 8 here.  B200AWQ_EUNSUPPORTED unless K % 512 == 0,
+ * N % 32 == 0, G % 64 == 0. */
+int b200awq_topk_softmax(const float* gating_output, float* topk_weights, int32_t* topk_ids,
+                         int32_t* token_expert_indices, int M, int E, int topk, b200awq_stream_t stream);
+int b200awq_moe_align_block_size(const int32_t* topk_ids, int numel, int num_experts, int block_size,
+                                 int32_t* sorted_ids, int32_t* expert_ids, int32_t* num_tokens_post_pad,
+                                 b200awq_stream_t stream);
+int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int32_t* qweight, const void* scales,
+                                 const int32_t* qzeros, const float* topk_weights, const int32_t* sorted_ids,
+                                 const int32_t* expert_ids, const int32_t* num_tokens_post_pad, void* y, int T, int topk,
+                                 int sorted_len, int K, int N, int group_size, int mul_weights, int block_size,
+                                 b200awq_stream_t stream);
+
 /* Tuning / debug knobs (process-global; used by the micro-benchmarks and layout self-tests).
  *   key 0: GEMV rows per warp override: 32 / 64 / 128 (0 = heuristic)
  *   key 1: tensor-core path split-K override (0 = heuristic)

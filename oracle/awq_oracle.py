@@ -286,3 +286,75 @@ def make_case(K: int, N: int, group_size: int, seed: int, raw: bool = False):
         scales = (np.abs(rng.standard_normal((K // G, N))) * 0.01 + 1e-3).astype(np.float16)
         qweight, qzeros = pack_gemm(iw, iz)
     return dict(intweight=iw, zeros=iz, scales=scales, qweight=qweight, qzeros=qzeros, group_size=G)
+
+
+# ------------------------------------------------------------------------------------- MoE
+# The reference's MoE kernels live in the un-vendored `autoawq-kernels` package (vLLM lineage); what is restated
+# here is the contract its call sites define (awq/modules/fused/moe.py:45-171) - parity unpinned by the reference.
+def topk_softmax(gating_output, topk: int):
+    """awq_ext.topk_softmax as fused_topk uses it (moe.py:137-171): softmax over the experts in fp32, the `topk`
+    largest probabilities per token (ties -> lower expert index), NOT renormalised (fused_topk does that itself).
+    Returns (topk_weights [M, topk] f32, topk_ids [M, topk] i32, token_expert_indices [M, topk] i32 = k * M + m)."""
+    g = np.asarray(gating_output, dtype=np.float32)
+    M, E = g.shape
+    e = np.exp((g - g.max(axis=1, keepdims=True)).astype(np.float64))
+    p = (e / e.sum(axis=1, keepdims=True)).astype(np.float32)
+    ids = np.zeros((M, topk), dtype=np.int32)
+    w = np.zeros((M, topk), dtype=np.float32)
+    work = p.copy()
+    for k in range(topk):
+        j = work.argmax(axis=1)  # first maximum = lowest index
+        ids[:, k] = j
+        w[:, k] = p[np.arange(M), j]
+        work[np.arange(M), j] = -1.0
+    src = (np.arange(topk, dtype=np.int32)[None, :] * M + np.arange(M, dtype=np.int32)[:, None]).astype(np.int32)
+    return w, ids, src
+
+
+def moe_align_block_size(topk_ids, block_size: int, num_experts: int):
+    """moe_align_block_size (moe.py:92-134, including its worked example): flattened slot indices grouped by expert in
+    ascending slot order, each expert's run padded with the sentinel `numel` to a multiple of block_size.
+    Returns (sorted_ids [numel + E*(block_size-1)] i32, expert_ids [numel + E] i32 (one per block; unused tail left
+    at -1 here, uninitialised in the reference), num_tokens_post_padded int)."""
+    flat = np.asarray(topk_ids, dtype=np.int64).reshape(-1)
+    numel = flat.size
+    sorted_ids = np.full(numel + num_experts * (block_size - 1), numel, dtype=np.int32)
+    expert_ids = np.full(numel + num_experts, -1, dtype=np.int32)
+    pos = 0
+    blk = 0
+    for e in range(num_experts):
+        idx = np.nonzero(flat == e)[0]
+        if idx.size == 0:
+            continue
+        padded = -(-idx.size // block_size) * block_size
+        sorted_ids[pos:pos + idx.size] = idx
+        expert_ids[blk:blk + padded // block_size] = e
+        pos += padded
+        blk += padded // block_size
+    return sorted_ids, expert_ids, pos
+
+
+def grouped_gemm_f64(x, w_ekn, topk_weights, sorted_ids, expert_ids, num_post_padded: int, mul_weights: bool,
+                     block_size: int = 16):
+    """awq_ext.grouped_gemm_forward as apply_moe_weights calls it (moe.py:60-89): for every real slot id in the
+    sorted list, out[id // topk, id % topk, :] = x_row(id) . W[expert of its block] (* topk_weights.flat[id] when
+    mul_weights), x_row(id) = x[id // topk, 0] for x [T, 1, K] and x.reshape(-1, K)[id] for x [T, topk, K].
+    `w_ekn` = dequantised expert weights [E, K, N] (dequantize_gemm per expert).  fp64; rows of slots that are
+    never listed stay zero."""
+    x = np.asarray(x)
+    T, topk = np.asarray(topk_weights).shape
+    K = x.shape[-1]
+    N = w_ekn.shape[-1]
+    xr = x.reshape(-1, K).astype(np.float64)
+    per_slot = x.shape[1] != 1
+    out = np.zeros((T * topk, N), dtype=np.float64)
+    tw = np.asarray(topk_weights, dtype=np.float64).reshape(-1)
+    for s in range(num_post_padded):
+        i = int(sorted_ids[s])
+        if i >= T * topk:
+            continue
+        e = int(expert_ids[s // block_size])
+        row = xr[i if per_slot else i // topk]
+        y = row @ w_ekn[e].astype(np.float64)
+        out[i] = y * tw[i] if mul_weights else y
+    return out.reshape(T, topk, N)

@@ -129,3 +129,38 @@ def test_column_concat_is_format_preserving():
     wa = O.dequantize_gemm(a["qweight"], a["qzeros"], a["scales"], 32)
     wb = O.dequantize_gemm(b["qweight"], b["qzeros"], b["scales"], 32)
     assert np.array_equal(_bits(w), _bits(np.concatenate([wa, wb], axis=1)))
+
+
+def test_moe_align_oracle_matches_reference_docstring_example():
+    """awq/modules/fused/moe.py:104-113 spells out one worked example; it is the only vector the reference holds for
+    the MoE path, so the oracle is pinned to it."""
+    import numpy as np
+
+    from oracle import awq_oracle as O
+
+    ids = np.array([[2, 3, 4], [1, 2, 4], [1, 3, 4], [1, 2, 3]])
+    s, e, n = O.moe_align_block_size(ids, 4, 5)
+    assert n == 16 and s[:16].tolist() == [3, 6, 9, 12, 0, 4, 10, 12, 1, 7, 11, 12, 2, 5, 8, 12]
+    assert e[:4].tolist() == [1, 2, 3, 4]
+
+
+def test_moe_topk_and_grouped_gemm_oracle_self_consistency():
+    import numpy as np
+
+    from oracle import awq_oracle as O
+
+    g = np.array([[0.0, 1.0, 1.0, -1.0]], dtype=np.float32)
+    w, i, src = O.topk_softmax(g, 2)
+    assert i.tolist() == [[1, 2]] and abs(float(w.sum()) - 2 * float(w[0, 0])) < 1e-7 and src.tolist() == [[0, 1]]
+    # grouped GEMM == per-token dense matmul with the selected expert
+    rng = np.random.default_rng(0)
+    E, K, N, T, topk = 3, 8, 4, 4, 2
+    W = rng.standard_normal((E, K, N))
+    x = rng.standard_normal((T, 1, K))
+    ids = np.array([[0, 1], [2, 0], [1, 2], [0, 2]])
+    tw = rng.random((T, topk))
+    s, e, n = O.moe_align_block_size(ids, 16, E)
+    out = O.grouped_gemm_f64(x, W, tw, s, e, n, True)
+    for t in range(T):
+        for k in range(topk):
+            np.testing.assert_allclose(out[t, k], x[t, 0] @ W[ids[t, k]] * tw[t, k], rtol=1e-12)
