@@ -161,6 +161,29 @@ def test_program_replays_and_leaves_scratch_clean(api, small_blocks):
         assert int(ws.count_nonzero()) == 0, "program left the shared workspace dirty"
 
 
+def test_program_is_bit_reproducible(api):
+    """The split-K sums travel as integers (csrc/program.cu, packed hand-off): the result does not depend on the order
+    in which CTAs arrive, so two runs on the same input must agree bit for bit - at the Llama-3-8B shapes, where
+    every column block has ~10 contributors."""
+    from autoawq_b200.program import DecodeProgram
+
+    blocks = [Block(4096, 14336, 6144, 128, seed=21)]
+    h = _h0(4096, 1, seed=13)
+    prog = DecodeProgram()
+    bufs = _record(prog, blocks, h, 1)
+    prog.build()
+    assert prog.fused
+    prog.run()
+    torch.cuda.synchronize()
+    first = {k: v.clone() for k, v in bufs[0].items()}
+    for _ in range(4):
+        prog.run()
+        torch.cuda.synchronize()
+        for k, v in bufs[0].items():
+            assert torch.equal(v, first[k]), f"{k} differs between two runs of the same program"
+    _no_abort("reproducibility")
+
+
 def test_program_in_cuda_graph(api, small_blocks):
     from autoawq_b200.program import DecodeProgram
 
