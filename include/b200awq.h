@@ -119,7 +119,11 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *   key 3: 1 = the persistent GEMV records per-CTA phase timestamps (read with b200awq_debug_read);
  *          2 = the decode-program kernel records per-op phase timestamps of its first 8 CTAs / 32 ops
  *          (b200awq_debug_read then returns [op][cta][8] uint64 ns: op begin, previous op complete, activations
- *          staged, first tile landed, warp 0 done, all warps done, partial sums added, published)
+ *          staged, first tile landed, warp 0 done, all warps done, partial sums pushed, next op's loads released);
+ *          3 = b200awq_debug_read returns the decode-program kernel's abort record instead: int32 [0..3] = {code, op,
+ *          CTA, aborted} of the first wait that exceeded 0.5 s (every spin loop of that kernel gives up rather than
+ *          hang the GPU), then per CTA 10 ints = (code << 16 | op) of the wait each warp abandoned;
+ *          4 = the decode-program kernel does not recycle its accumulator rows (inspection with tools/program_debug.py)
  *   key 4: 1 = launch every kernel with the programmatic-dependent-launch attribute (the kernels issue
  *          their weight loads before griddepcontrol.wait, so consecutive linears overlap); default 0
  *   key 5: 1 = disable the persistent TMA-ring GEMV (use the register-staged GEMV for every M <= 8 shape)
@@ -128,7 +132,11 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *          tail of each kernel); default 0 - it measured slightly slower on B200
  *   key 7: 1 = stage the activations in shared memory in the persistent GEMV (M <= 2); default 0
  *   key 8: persistent GEMV L2-prefetch distance + 1 in tiles (0 / 1 = off, the default)
- *   key 9: persistent GEMV ring stages per consumer warp for M = 1 (1 / 2; 0 = default 3)
+ *   key 9: persistent GEMV ring stages per consumer warp for M = 1 (1 / 2; 0 = default 3); the decode-program
+ *          kernel uses 1 stage per warp when this is 1 (default 2)
+ *   key 10: decode program: 2 = do NOT hold the next op's weight loads back until the CTA has pushed its sums of
+ *           the previous op (default: hold them back, +9 % measured)
+ *   key 11: decode program: 2 = no back-off in the duty warp's polls (default: 400 ns sleep between attempts)
  */
 int b200awq_set_knob(int key, int value);
 int b200awq_get_knob(int key);
