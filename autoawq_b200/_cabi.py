@@ -67,7 +67,7 @@ SIGNATURES = {
     "b200awq_grouped_gemm_forward": (
         _c_int,
         [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-         _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p],
+         _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p],
     ),
     "b200awq_program_create": (_c_int, [ctypes.POINTER(Op), _c_int, ctypes.POINTER(_c_void_p)]),
     "b200awq_program_num_ops": (_c_int, [_c_void_p]),

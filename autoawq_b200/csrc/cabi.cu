@@ -213,17 +213,31 @@ int b200awq_moe_align_block_size(const int32_t* topk_ids, int numel, int num_exp
 int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int32_t* qweight, const void* scales,
                                  const int32_t* qzeros, const float* topk_weights, const int32_t* sorted_ids,
                                  const int32_t* expert_ids, const int32_t* num_tokens_post_pad, void* y, int T, int topk,
-                                 int sorted_len, int K, int N, int group_size, int mul_weights, int block_size,
-                                 b200awq_stream_t stream) {
+                                 int sorted_len, int E, int K, int N, int group_size, int mul_weights, int block_size,
+                                 void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
   const int G = group_size <= 0 ? K : group_size;
-  if (T < 0 || topk <= 0 || sorted_len < 0 || !shape_ok(1, K, N, G) || block_size <= 0) return B200AWQ_EINVAL;
+  if (T < 0 || topk <= 0 || sorted_len < 0 || E <= 0 || !shape_ok(1, K, N, G) || block_size <= 0) return B200AWQ_EINVAL;
   if (x_rows_per_token != 1 && x_rows_per_token != topk) return B200AWQ_EINVAL;
   if (T == 0) return B200AWQ_OK;
   if (!x || !qweight || !scales || !qzeros || !topk_weights || !sorted_ids || !expert_ids || !num_tokens_post_pad || !y)
     return B200AWQ_EINVAL;
-  if (!moe_grouped_supported(K, N, G) || (block_size % 8) != 0) return B200AWQ_EUNSUPPORTED;
+  if ((block_size % 8) != 0) return B200AWQ_EUNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int hbs = sorted_len / 8;
+  // decode-sized problems: the persistent TMA-ring GEMV, one job per 8 sorted slots (needs 8 rows of fp32 scratch
+  // per job); anything larger, or without a workspace: the register-staged grouped kernel
+  const size_t need = kTicketBytes + (size_t)hbs * 8 * N * sizeof(float);
+  if (knob(12) != 2 && hbs > 0 && workspace != nullptr && workspace_bytes >= need &&
+      (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && gemv_v3_moe_supported(K, N, G, hbs)) {
+    int* tickets = reinterpret_cast<int*>(workspace);
+    float* acc = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kTicketBytes);
+    return fold(gemv_v3_moe(x, x_rows_per_token == 1 ? 0 : 1, qweight, scales, qzeros, mul_weights ? topk_weights : nullptr,
+                            sorted_ids, expert_ids, num_tokens_post_pad, y, T * topk, topk, hbs, E, K, N, G, block_size,
+                            acc, tickets, st));
+  }
+  if (!moe_grouped_supported(K, N, G)) return B200AWQ_EUNSUPPORTED;
   return fold(moe_grouped_gemm(x, x_rows_per_token == 1 ? 0 : 1, qweight, scales, qzeros, topk_weights, sorted_ids,
                                expert_ids, num_tokens_post_pad, y, T * topk, topk, sorted_len, K, N, G, mul_weights,
-                               block_size, static_cast<cudaStream_t>(stream)));
+                               block_size, st));
 }
 }  // extern "C"

@@ -321,14 +321,42 @@ cudaError_t gemv_v3_debug_read(void* dst, size_t bytes) {
 }
 
 
-template <int MT, int SPW, bool XS>
+// Grouped (MoE) variant, template flag MOE: blockIdx.y = job = eight sorted slots of one expert
+// (awq/modules/fused/moe.py:60-89).  The stacked expert weights [E, K, N/8] are ONE 2-D tensor map of E*K rows, so the
+// expert is a row offset in the tile coordinate; activations are gathered and outputs scattered through the sorted
+// slot ids; split-K scratch and tickets are per job.
+struct V3Moe {
+  const int* sorted_ids;
+  const int* expert_ids;
+  const int* num_post_pad;
+  const float* topk_w;     // routing weights [n_slots] or nullptr (mul_weights = false)
+  int n_slots, topk, x_per_slot, block_size;
+};
+
+template <int MT, int SPW, bool XS, bool MOE = false>
 __global__ void __launch_bounds__(kV3Threads, 1)
     gemv_v3_kernel(const __grid_constant__ CUtensorMap tmw, const __half* __restrict__ x, int64_t ldx,
                    const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                    const __half* __restrict__ bias, __half* __restrict__ y, float* __restrict__ acc_ws,
                    int* __restrict__ tickets, int M, int K, int N, int G, int g_shift,
-                   const uint8_t* __restrict__ next_w, long long next_bytes, int dbg, int l2_ahead) {
+                   const uint8_t* __restrict__ next_w, long long next_bytes, int dbg, int l2_ahead, const V3Moe moe) {
   constexpr int NS = V3Smem<MT, SPW>::kStages;
+  __shared__ int s_slot[8];       // MOE: output row of each of the job's slots (-1 = padding)
+  int row_off = 0;                // MOE: first row of the job's expert in the stacked tensor
+  if (MOE) {
+    const int job = blockIdx.y;
+    if (job * 8 >= *moe.num_post_pad) return;
+    if (threadIdx.x < 8) {
+      const int id = moe.sorted_ids[job * 8 + threadIdx.x];
+      s_slot[threadIdx.x] = id < moe.n_slots ? id : -1;
+    }
+    const int e = moe.expert_ids[(job * 8) / moe.block_size];
+    row_off = e * K;
+    scales += (int64_t)e * (K / G) * N;
+    qzeros += (int64_t)e * (K / G) * (N >> 3);
+    acc_ws += (int64_t)job * 8 * N;
+    tickets += job * (N / kV3TileCols);
+  }
   extern __shared__ __align__(1024) uint8_t v3_smem[];
   uint8_t* ring = v3_smem;                                   // NS x 8 KB weight tiles (1 KB aligned: swizzle atoms)
   uint8_t* aux = v3_smem + (size_t)NS * kV3TileBytes;        // NS x (256 scales + 32 zero words)
@@ -364,6 +392,12 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   }
   for (int i = tid; i < V3Smem<MT, SPW>::colacc_floats; i += kV3Threads) colacc[i] = 0.f;
   __syncthreads();
+  if (MOE) {
+    bool any = false;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) any = any || s_slot[m] >= 0;
+    if (!any) return;   // pure padding (uniform)
+  }
 
   if (warp == 0) {
     // ============================================================ producer: weights never wait for PDL
@@ -378,7 +412,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       const int kL2Ahead = l2_ahead > 0 ? SPW + l2_ahead : 0;  // 0: no L2 prefetch
       int cbp = a / TPC, ktp = a - cbp * TPC;      // prefetch cursor (no per-tile divisions)
       auto pf_one = [&]() {
-        tma_prefetch_l2_2d(&tmw, cbp * (kV3TileCols / 8), ktp * kV3TileRows);
+        tma_prefetch_l2_2d(&tmw, cbp * (kV3TileCols / 8), row_off + ktp * kV3TileRows);
         if (++ktp == TPC) { ktp = 0; ++cbp; }
       };
       for (int tp = a; tp < bnd && tp < a + kL2Ahead; ++tp) pf_one();
@@ -394,7 +428,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
         uint8_t* st = ring + (size_t)stage * kV3TileBytes;
         uint8_t* sa = aux + (size_t)stage * kV3AuxBytes;
         mbar_arrive_expect_tx(&full[stage], kV3TileBytes + kV3AuxBytes);
-        tma_load_2d(st, &tmw, &full[stage], cb * (kV3TileCols / 8), kt * kV3TileRows);
+        tma_load_2d(st, &tmw, &full[stage], cb * (kV3TileCols / 8), row_off + kt * kV3TileRows);
         bulk_load_1d(sa, scales + (int64_t)grp_abs * N + cb * kV3TileCols, kV3ScaleBytes, &full[stage]);
         bulk_load_1d(sa + kV3ScaleBytes, qzeros + (int64_t)grp_abs * NW + cb * (kV3TileCols / 8), kV3ZeroBytes,
                      &full[stage]);
@@ -418,7 +452,16 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   const int cw = warp - 1;             // 0..7
   const int ct = tid - 32;             // 0..255
   const int g = lane >> 2, tig = lane & 3;
-  const bool tok_ok = g < M;
+  const int my_slot = MOE ? s_slot[g] : 0;
+  const bool tok_ok = MOE ? my_slot >= 0 : g < M;
+  // this lane's token row: row g of x, or (MOE) the row the slot's id names
+  const __half* xrow = MOE ? x + (int64_t)(tok_ok ? (moe.x_per_slot ? my_slot : my_slot / moe.topk) : 0) * K
+                           : x + (int64_t)g * ldx;
+  V3Scatter scat;
+  if (MOE) {
+    scat.ids = s_slot;
+    scat.tw = moe.topk_w;
+  }
   float* my_red = red + (size_t)cw * MT * kGvRedStride;
   float* my_col = colacc + (size_t)cw * MT * kV3TileCols;
   const int a_w = t0 + (int)((int64_t)ntile * cw / kV3Warps);
@@ -440,7 +483,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
           xb[bb][1] = *reinterpret_cast<const uint32_t*>(px + 16 * bb + 8);
         }
       } else {
-        const __half* px = x + (int64_t)g * ldx + ktile * kV3TileRows + 2 * tig;
+        const __half* px = xrow + ktile * kV3TileRows + 2 * tig;
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
           xb[bb][0] = *reinterpret_cast<const uint32_t*>(px + 16 * bb);
@@ -487,7 +530,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       if (cur_cb >= 0 && ntl > 0) {
         // this warp's run crosses a column block: push its pending sums alone (rare)
         __syncwarp();
-        v3_push_warp<MT>(my_col, cur_cb, ntl, TPC, lane, bias, y, acc_ws, tickets, M, N);
+        v3_push_warp<MT>(my_col, cur_cb, ntl, TPC, lane, bias, y, acc_ws, tickets, M, N, scat);
       }
       cur_cb = cb;
       ntl = 0;
@@ -535,7 +578,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       while (w1 < kV3Warps && warp_cb[w1] == cbg) ++w1;
       if (cbg >= 0)
         v3_add_cols<MT, kV3Warps * 32>(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cbg, ct, acc_ws,
-                                       M, N);
+                                       M, N, scat);
       w0 = w1;
     }
   }
@@ -558,7 +601,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   // pass 3: finalise the blocks for which this CTA was the last contributor
 #pragma unroll 1
   for (int w = 0; w < kV3Warps; ++w)
-    if (flags[w]) v3_finalize<MT, kV3Warps * 32>(warp_cb[w], ct, bias, y, acc_ws, tickets, M, N);
+    if (flags[w]) v3_finalize<MT, kV3Warps * 32>(warp_cb[w], ct, bias, y, acc_ws, tickets, M, N, scat);
   if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 7] = gtimer();
 }
 
@@ -616,7 +659,42 @@ static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cud
   return launch_kernel(kern, dim3(grid), dim3(kV3Threads), smem, st, tm, reinterpret_cast<const __half*>(a.x), a.ldx,
                        reinterpret_cast<const __half*>(a.scales), a.qzeros, reinterpret_cast<const __half*>(a.bias),
                        reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M, a.K, a.N, a.G, g_shift,
-                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3) == 1 ? 1 : 0, knob(8) > 0 ? knob(8) - 1 : 0);
+                       reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3) == 1 ? 1 : 0, knob(8) > 0 ? knob(8) - 1 : 0,
+                       V3Moe{});
+}
+
+// Grouped launch: grid.y = sorted_len / 8 jobs (most of them padding: they exit at once).  Needs hbs * 8 rows of fp32
+// scratch and hbs * N/256 tickets; the caller checks that.
+cudaError_t gemv_v3_moe(const void* x, int x_per_slot, const int32_t* qweight, const void* scales, const int32_t* qzeros,
+                        const float* topk_w, const int* sorted_ids, const int* expert_ids, const int* num_post_pad,
+                        void* y, int n_slots, int topk, int hbs, int E, int K, int N, int G, int block_size,
+                        float* acc_ws, int* tickets, cudaStream_t st) {
+  int g_shift = 31;
+  if ((G & (G - 1)) == 0) {
+    g_shift = 0;
+    while ((1 << g_shift) < G) ++g_shift;
+  }
+  CUtensorMap tm;
+  cudaError_t e = make_tmap_2d(qweight, /*int32*/ 1, (uint64_t)(N / 8), (uint64_t)E * K, (uint64_t)(N / 8) * 4, 32,
+                               kV3TileRows, &tm);
+  if (e != cudaSuccess) return e;
+  auto kern = gemv_v3_kernel<8, 1, false, true>;
+  const size_t smem = V3Smem<8, 1>::bytes;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int T = (N / kV3TileCols) * (K / kV3TileRows);
+  const int grid = T < v3_sm_count() ? T : v3_sm_count();
+  V3Moe moe{sorted_ids, expert_ids, num_post_pad, topk_w, n_slots, topk, x_per_slot, block_size};
+  return launch_kernel(kern, dim3(grid, hbs), dim3(kV3Threads), smem, st, tm, reinterpret_cast<const __half*>(x),
+                       (int64_t)K, reinterpret_cast<const __half*>(scales), qzeros, static_cast<const __half*>(nullptr),
+                       reinterpret_cast<__half*>(y), acc_ws, tickets, 8, K, N, G, g_shift,
+                       static_cast<const uint8_t*>(nullptr), 0LL, 0, 0, moe);
+}
+
+bool gemv_v3_moe_supported(int K, int N, int G, int hbs) {
+  const bool g_ok = ((G & (G - 1)) == 0) || G == K;
+  return (N % kV3TileCols) == 0 && (K % kV3TileRows) == 0 && (G % kV3TileRows) == 0 && (K % G) == 0 && g_ok &&
+         (int64_t)hbs * (N / kV3TileCols) <= (int64_t)(kTicketBytes / sizeof(int));
 }
 
 // Shapes the persistent TMA-ring kernel takes: whole 64 x 256 tiles inside one quantisation group.

@@ -48,13 +48,19 @@ struct V3Smem {
 
 // Shared by the warp-level (NT = 32) and CTA-level (NT = 256) pushes: add `cols` [MT][256] (shared memory,
 // summed over `nsrc` sources `src_stride` floats apart) into the fp32 workspace (relaxed REDs).
+// Output scatter of the grouped (MoE) variant: token m of the CTA's job goes to row ids[m] of y (ids in shared
+// memory, -1 = padding slot), optionally scaled by the routing weight tw[ids[m]].  ids == nullptr: row m, as is.
+struct V3Scatter {
+  const int* ids = nullptr;
+  const float* tw = nullptr;
+};
 template <int MT, int NT>
 __device__ __forceinline__ void v3_add_cols(float* cols, int nsrc, int src_stride, int cb, int t,
-                                            float* __restrict__ acc_ws, int M, int N) {
+                                            float* __restrict__ acc_ws, int M, int N, V3Scatter sc = V3Scatter()) {
   const int n_base = cb * kV3TileCols;
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
-    if (m < M) {
+    if (m < M && (sc.ids == nullptr || sc.ids[m] >= 0)) {   // padding slots carry exact zeros: nothing to add
       for (int c = t; c < kV3TileCols; c += NT) {
         float v = 0.f;
         for (int sidx = 0; sidx < nsrc; ++sidx) {
@@ -69,18 +75,27 @@ __device__ __forceinline__ void v3_add_cols(float* cols, int nsrc, int src_strid
 // The last contributor of column block `cb` rounds to fp16 (+ bias) and restores the zeros.
 template <int MT, int NT>
 __device__ __forceinline__ void v3_finalize(int cb, int t, const __half* __restrict__ bias, __half* __restrict__ y,
-                                            float* __restrict__ acc_ws, int* __restrict__ tickets, int M, int N) {
+                                            float* __restrict__ acc_ws, int* __restrict__ tickets, int M, int N,
+                                            V3Scatter sc = V3Scatter()) {
   const int n_base = cb * kV3TileCols;
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
     if (m < M) {
+      int row = m;
+      float mulw = 1.f;
+      if (sc.ids != nullptr) {
+        row = sc.ids[m];
+        if (row < 0) continue;   // padding slot: nothing was added for it
+        if (sc.tw != nullptr) mulw = sc.tw[row];
+      }
       for (int c = t; c < kV3TileCols; c += NT) {
         const int n = n_base + c;
         float* p = &acc_ws[(int64_t)m * N + n];
         float v = ld_relaxed_f32(p);
         *p = 0.f;
         if (bias != nullptr) v += __half2float(bias[n]);
-        y[(int64_t)m * N + n] = __float2half_rn(v);
+        if (sc.ids != nullptr) v *= mulw;
+        y[(int64_t)row * N + n] = __float2half_rn(v);
       }
     }
   }
@@ -90,13 +105,14 @@ __device__ __forceinline__ void v3_finalize(int cb, int t, const __half* __restr
 template <int MT>
 __device__ __forceinline__ bool v3_push_warp(float* cols, int cb, int ntl, int TPC, int lane,
                                              const __half* __restrict__ bias, __half* __restrict__ y,
-                                             float* __restrict__ acc_ws, int* __restrict__ tickets, int M, int N) {
-  v3_add_cols<MT, 32>(cols, 1, 0, cb, lane, acc_ws, M, N);
+                                             float* __restrict__ acc_ws, int* __restrict__ tickets, int M, int N,
+                                             V3Scatter sc = V3Scatter()) {
+  v3_add_cols<MT, 32>(cols, 1, 0, cb, lane, acc_ws, M, N, sc);
   __syncwarp();
   int last = 0;
   if (lane == 0) last = (atom_add_acq_rel(&tickets[cb], ntl) + ntl == TPC);
   last = __shfl_sync(0xffffffffu, last, 0);
-  if (last) v3_finalize<MT, 32>(cb, lane, bias, y, acc_ws, tickets, M, N);
+  if (last) v3_finalize<MT, 32>(cb, lane, bias, y, acc_ws, tickets, M, N, sc);
   return last != 0;
 }
 

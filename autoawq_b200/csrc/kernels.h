@@ -87,6 +87,13 @@ void program_destroy(Program* p);
 cudaError_t program_debug_read(void* dst, size_t bytes);
 cudaError_t program_abort_read(void* dst, size_t bytes);
 
+// grouped persistent GEMV (gemv.cu): the decode-size path of grouped_gemm_forward
+bool gemv_v3_moe_supported(int K, int N, int G, int hbs);
+cudaError_t gemv_v3_moe(const void* x, int x_per_slot, const int32_t* qweight, const void* scales, const int32_t* qzeros,
+                        const float* topk_w, const int* sorted_ids, const int* expert_ids, const int* num_post_pad,
+                        void* y, int n_slots, int topk, int hbs, int E, int K, int N, int G, int block_size,
+                        float* acc_ws, int* tickets, cudaStream_t st);
+
 // MoE (moe.cu)
 cudaError_t topk_softmax(const float* gating, float* topk_w, int* topk_ids, int* src_rows, int M, int E, int topk,
                          cudaStream_t st);

@@ -246,11 +246,18 @@ def grouped_gemm_forward(x, qweight, scales, qzeros, topk_weights, sorted_token_
         raise B200AwqError(f"b200awq: x {tuple(x.shape)} does not match T={T}, topk={topk}, K={K}")
     y = torch.empty((T, topk, N), dtype=torch.float16, device=x.device)
     with _DeviceGuard(x.device):
+        st = _stream(x.device)
+        slen = sorted_token_ids.numel()
+        # decode-sized calls get the split-K scratch of the persistent kernel (8 rows of fp32 per 8 sorted slots);
+        # beyond 64 MB of scratch the library's workspace-free grouped kernel runs instead
+        need = 16384 + slen * N * 4
+        ws = _workspace(x.device, st, need) if need <= (64 << 20) else None
         code = lib.b200awq_grouped_gemm_forward(
             xc.data_ptr(), int(xc.shape[1]), qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(),
             topk_weights.data_ptr(), sorted_token_ids.data_ptr(), expert_ids.data_ptr(),
-            num_tokens_post_padded.data_ptr(), y.data_ptr(), T, topk, sorted_token_ids.numel(), K, N, G,
-            1 if mul_weights else 0, 16, _stream(x.device))
+            num_tokens_post_padded.data_ptr(), y.data_ptr(), T, topk, slen, E, K, N, G,
+            1 if mul_weights else 0, 16, ws.data_ptr() if ws is not None else None,
+            ws.numel() if ws is not None else 0, st)
     check(code, f"b200awq_grouped_gemm_forward(T={T}, topk={topk}, E={E}, K={K}, N={N}, G={G})")
     return y
 

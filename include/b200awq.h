@@ -99,8 +99,11 @@ int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200aw
  * y[id] = x_row(id) . deq(W[expert_ids[pos / block_size]]) (* topk_weights[id] if mul_weights), x_row(id) = x[id /
  * topk] when x_rows_per_token == 1 (x [T, 1, K]) and x[id] when x_rows_per_token == topk (x [T, topk, K]).
  * qweight [E, K, N/8], scales [E, K/G, N], qzeros [E, K/G, N/8] (stacked GEMM layout).  block_size is 16 at the
- * reference's call site (moe.py:54-56) and must be a multiple of 8 here.  B200AWQ_EUNSUPPORTED unless K % 512 == 0,
- * N % 32 == 0, G % 64 == 0. */
+ * reference's call site (moe.py:54-56) and must be a multiple of 8 here.  Two kernels: with a workspace of
+ * b200awq_workspace_bytes(sorted_len, K, N) bytes (zero-initialised, left zero; the per-op workspace serves) and
+ * N % 256 == 0, K % 64 == 0, G in {64, 128, K} the persistent TMA-ring GEMV runs one job per 8 sorted slots (the
+ * decode case); otherwise a register-staged grouped kernel (K % 512 == 0, N % 32 == 0, G % 64 == 0), else
+ * B200AWQ_EUNSUPPORTED.  Knob 12 = 2 forces the second kernel. */
 int b200awq_topk_softmax(const float* gating_output, float* topk_weights, int32_t* topk_ids,
                          int32_t* token_expert_indices, int M, int E, int topk, b200awq_stream_t stream);
 int b200awq_moe_align_block_size(const int32_t* topk_ids, int numel, int num_experts, int block_size,
@@ -109,8 +112,8 @@ int b200awq_moe_align_block_size(const int32_t* topk_ids, int numel, int num_exp
 int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int32_t* qweight, const void* scales,
                                  const int32_t* qzeros, const float* topk_weights, const int32_t* sorted_ids,
                                  const int32_t* expert_ids, const int32_t* num_tokens_post_pad, void* y, int T, int topk,
-                                 int sorted_len, int K, int N, int group_size, int mul_weights, int block_size,
-                                 b200awq_stream_t stream);
+                                 int sorted_len, int E, int K, int N, int group_size, int mul_weights, int block_size,
+                                 void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
 
 /* Tuning / debug knobs (process-global; used by the micro-benchmarks and layout self-tests).
  *   key 0: GEMV rows per warp override: 32 / 64 / 128 (0 = heuristic)

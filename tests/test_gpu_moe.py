@@ -86,9 +86,24 @@ def _experts(E, K, N, G, seed):
     return np.stack(qw), np.stack(qz), np.stack(sc), np.stack(w)
 
 
-@pytest.mark.parametrize("T,topk,E,K,N,G", [(1, 2, 8, 1024, 512, 128), (5, 2, 8, 1024, 512, 128),
-                                             (37, 2, 4, 512, 256, 64), (3, 3, 6, 1536, 96, 128)])
-def test_grouped_gemm_and_full_moe_block(awq_ext, T, topk, E, K, N, G):
+@pytest.mark.parametrize("T,topk,E,K,N,G,kernel", [
+    (1, 2, 8, 1024, 512, 128, "ring"), (5, 2, 8, 1024, 512, 128, "ring"), (37, 2, 4, 512, 256, 64, "ring"),
+    (3, 3, 6, 1536, 96, 128, "staged"),            # N not a multiple of 256: the register-staged kernel
+    (5, 2, 8, 1024, 512, 128, "staged-forced"),    # knob 12 = 2
+])
+def test_grouped_gemm_and_full_moe_block(awq_ext, T, topk, E, K, N, G, kernel):
+    from autoawq_b200 import ext
+
+    ext.set_knob(12, 2 if kernel == "staged-forced" else 0)
+    try:
+        _moe_block(awq_ext, T, topk, E, K, N, G)
+    finally:
+        ext.set_knob(12, 0)
+    for ws in ext._WS.values():
+        assert int(ws.count_nonzero()) == 0, "grouped GEMM left the shared workspace dirty"
+
+
+def _moe_block(awq_ext, T, topk, E, K, N, G):
     """apply_moe_weights (moe.py:45-89) end to end: route, align, gate|up grouped GEMM, silu*mul, down grouped GEMM
     with the routing weights, sum over the top-k - every stage against the oracle on the GPU's own inputs."""
     rng = np.random.default_rng(T * 100 + E)

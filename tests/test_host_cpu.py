@@ -210,7 +210,8 @@ def test_moe_argument_validation_without_gpu(built):
     assert lib.b200awq_topk_softmax(None, None, None, None, 4, 8, 2, None) == 1       # null pointers
     assert lib.b200awq_moe_align_block_size(None, 8, 8, 16, None, None, None, None) == 1
     p8 = (None,) * 8   # qweight, scales, qzeros, topk_weights, sorted_ids, expert_ids, num_post_pad, y
-    assert lib.b200awq_grouped_gemm_forward(None, 1, *p8, 0, 2, 0, 4096, 4096, 128, 0, 16, None) == 0   # T == 0
-    assert lib.b200awq_grouped_gemm_forward(None, 1, *p8, 1, 2, 32, 4096, 4095, 128, 0, 16, None) == 1  # N % 8 != 0
-    assert lib.b200awq_grouped_gemm_forward(None, 3, *p8, 1, 2, 32, 4096, 4096, 128, 0, 16, None) == 1  # rows/token
-    assert lib.b200awq_grouped_gemm_forward(None, 1, *p8, 1, 2, 32, 4096, 4096, 128, 0, 16, None) == 1  # null pointers
+    tail = (None, 0, None)   # workspace, workspace_bytes, stream
+    assert lib.b200awq_grouped_gemm_forward(None, 1, *p8, 0, 2, 0, 8, 4096, 4096, 128, 0, 16, *tail) == 0   # T == 0
+    assert lib.b200awq_grouped_gemm_forward(None, 1, *p8, 1, 2, 32, 8, 4096, 4095, 128, 0, 16, *tail) == 1  # N % 8 != 0
+    assert lib.b200awq_grouped_gemm_forward(None, 3, *p8, 1, 2, 32, 8, 4096, 4096, 128, 0, 16, *tail) == 1  # rows/token
+    assert lib.b200awq_grouped_gemm_forward(None, 1, *p8, 1, 2, 32, 8, 4096, 4096, 128, 0, 16, *tail) == 1  # null pointers
