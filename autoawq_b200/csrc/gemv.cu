@@ -678,17 +678,24 @@ cudaError_t gemv_v3_moe(const void* x, int x_per_slot, const int32_t* qweight, c
   cudaError_t e = make_tmap_2d(qweight, /*int32*/ 1, (uint64_t)(N / 8), (uint64_t)E * K, (uint64_t)(N / 8) * 4, 32,
                                kV3TileRows, &tm);
   if (e != cudaSuccess) return e;
-  auto kern = gemv_v3_kernel<8, 1, false, true>;
-  const size_t smem = V3Smem<8, 1>::bytes;
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   const int T = (N / kV3TileCols) * (K / kV3TileRows);
   const int grid = T < v3_sm_count() ? T : v3_sm_count();
   V3Moe moe{sorted_ids, expert_ids, num_post_pad, topk_w, n_slots, topk, x_per_slot, block_size};
-  return launch_kernel(kern, dim3(grid, hbs), dim3(kV3Threads), smem, st, tm, reinterpret_cast<const __half*>(x),
-                       (int64_t)K, reinterpret_cast<const __half*>(scales), qzeros, static_cast<const __half*>(nullptr),
-                       reinterpret_cast<__half*>(y), acc_ws, tickets, 8, K, N, G, g_shift,
-                       static_cast<const uint8_t*>(nullptr), 0LL, 0, 0, moe);
+  // a job holds at most min(8, tokens) real slots (a token picks an expert once) and they are a prefix of the job:
+  // few tokens -> the narrow variants, which afford more ring stages per warp
+  const int tokens = n_slots / (topk > 0 ? topk : 1);
+  auto go = [&](auto kern, size_t smem, int mt) -> cudaError_t {
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e2 != cudaSuccess) return e2;
+    return launch_kernel(kern, dim3(grid, hbs), dim3(kV3Threads), smem, st, tm, reinterpret_cast<const __half*>(x),
+                         (int64_t)K, reinterpret_cast<const __half*>(scales), qzeros, static_cast<const __half*>(nullptr),
+                         reinterpret_cast<__half*>(y), acc_ws, tickets, mt, K, N, G, g_shift,
+                         static_cast<const uint8_t*>(nullptr), 0LL, 0, 0, moe);
+  };
+  if (tokens <= 1) return go(gemv_v3_kernel<1, 3, false, true>, V3Smem<1, 3>::bytes, 1);
+  if (tokens <= 2) return go(gemv_v3_kernel<2, 2, false, true>, V3Smem<2, 2>::bytes, 2);
+  if (tokens <= 4) return go(gemv_v3_kernel<4, 2, false, true>, V3Smem<4, 2>::bytes, 4);
+  return go(gemv_v3_kernel<8, 1, false, true>, V3Smem<8, 1>::bytes, 8);
 }
 
 bool gemv_v3_moe_supported(int K, int N, int G, int hbs) {
