@@ -56,7 +56,8 @@ struct __align__(128) ProgOp {
   int prologue;
   float eps;
   int ext_dep;            // >= 0: the external source was written by that (older) op of this program
-  int pad;
+  int n_part;             // CTAs that share this op's tiles (the first n_part; 0 = all): small ops use fewer, so that
+                          // fewer CTAs add into each column block (knob 13 = minimum tiles per participating CTA)
 };
 static_assert(sizeof(ProgOp) == 256, "ProgOp layout");
 
@@ -287,8 +288,9 @@ __global__ void __launch_bounds__(kProgThreads, 1)
         const int NW = N >> 3;
         const int TPC = K / kV3TileRows;
         const int T = (N / kV3TileCols) * TPC;
-        const int t0 = (int)((int64_t)T * bid / nblk);
-        const int t1 = (int)((int64_t)T * (bid + 1) / nblk);
+        const int np = o->n_part > 0 ? o->n_part : nblk;
+        const int t0 = bid < np ? (int)((int64_t)T * bid / np) : 0;
+        const int t1 = bid < np ? (int)((int64_t)T * (bid + 1) / np) : 0;
         const int ntile = t1 - t0;
         const int a = t0 + (int)((int64_t)ntile * w / kV3Warps);
         const int bnd = t0 + (int)((int64_t)ntile * (w + 1) / kV3Warps);
@@ -449,8 +451,9 @@ __global__ void __launch_bounds__(kProgThreads, 1)
     const int K = o->K, N = o->N, G = o->G, g_shift = o->g_shift;
     const int TPC = K / kV3TileRows;
     const int T = (N / kV3TileCols) * TPC;
-    const int t0 = (int)((int64_t)T * bid / nblk);
-    const int t1 = (int)((int64_t)T * (bid + 1) / nblk);
+    const int np = o->n_part > 0 ? o->n_part : nblk;
+    const int t0 = bid < np ? (int)((int64_t)T * bid / np) : 0;
+    const int t1 = bid < np ? (int)((int64_t)T * (bid + 1) / np) : 0;
     const int ntile = t1 - t0;
     const int a_w = t0 + (int)((int64_t)ntile * cw / kV3Warps);
     const int b_w = t0 + (int)((int64_t)ntile * (cw + 1) / kV3Warps);
@@ -776,6 +779,12 @@ int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* c
     p.K = op.K;
     p.N = op.N;
     p.G = op.group_size;
+    if (knob(13) > 0) {
+      const int tiles = (op.N / kV3TileCols) * (op.K / kV3TileRows);
+      int np = tiles / knob(13);
+      if (np < 1) np = 1;
+      p.n_part = np < grid ? np : 0;
+    }
     p.g_shift = 31;
     if ((p.G & (p.G - 1)) == 0) {
       p.g_shift = 0;
