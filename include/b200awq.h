@@ -140,6 +140,9 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *   key 10: decode program: 2 = do NOT hold the next op's weight loads back until the CTA has pushed its sums of
  *           the previous op (default: hold them back, +9 % measured)
  *   key 11: decode program: 2 = no back-off in the duty warp's polls (default: 400 ns sleep between attempts)
+ *   key 12: 2 = grouped_gemm_forward always uses the register-staged grouped kernel
+ *   key 13: decode program (read at b200awq_program_create): minimum tiles per participating CTA; ops with fewer
+ *           tiles per CTA are shared by fewer CTAs (0 = every CTA takes part in every op, the default: measured best)
  */
 int b200awq_set_knob(int key, int value);
 int b200awq_get_knob(int key);
