@@ -208,9 +208,10 @@ __device__ __forceinline__ void prog_wait_smem(volatile int* flag, int target, i
     if (wd.tick(code, op)) break;
 }
 
-// "Row op % 4 is clean": normally read from the shared-memory flag the duty warp keeps ahead; if the flag lags (the
-// duty warp only refreshes it between its own waits) the waiting thread checks the global counter itself - a lost
-// wake-up here deadlocked the Llama-3-8B shapes.
+// "Row op % 4 is clean": normally read from the shared-memory flag the duty warp keeps ahead.  The duty warps are
+// within one iteration of each other (each waits for staged[i] of ALL CTAs), so the flag cannot lag behind what the
+// consumers need (tests/test_program_protocol_model.py); the direct check of the global counter is a defensive
+// fall-back that costs nothing on the fast path.
 __device__ __forceinline__ void prog_wait_row_clean(volatile int* red_ok, const int* zeroed, int op, int nblk) {
   ProgWatch wd;
   while (*red_ok < op) {
