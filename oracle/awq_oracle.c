@@ -81,3 +81,48 @@ void oracle_gemm_f64(const uint16_t* x, const uint16_t* w, double* y, int M, int
 
 uint16_t oracle_float_to_half(float f) { return float_to_half(f); }
 float oracle_half_to_float(uint16_t h) { return half_to_float(h); }
+
+/* ---- MoE routing (awq/modules/fused/moe.py:92-171): independent C restatement of the two index-producing steps ---- */
+
+/* moe_align_block_size (moe.py:92-134): slots grouped by expert in ascending slot order, each run padded with `numel`
+ * to a multiple of block_size.  sorted_ids holds numel + num_experts * (block_size - 1) entries (pre-filled here with
+ * numel), expert_ids numel + num_experts (pre-filled with -1).  Returns the padded length. */
+int oracle_moe_align_block_size(const int32_t* topk_ids, int numel, int num_experts, int block_size,
+                                int32_t* sorted_ids, int32_t* expert_ids) {
+  int pos = 0, blk = 0;
+  for (int i = 0; i < numel + num_experts * (block_size - 1); ++i) sorted_ids[i] = numel;
+  for (int i = 0; i < numel + num_experts; ++i) expert_ids[i] = -1;
+  for (int e = 0; e < num_experts; ++e) {
+    int cnt = 0;
+    for (int i = 0; i < numel; ++i)
+      if (topk_ids[i] == e) sorted_ids[pos + cnt++] = i;
+    if (cnt == 0) continue;
+    const int padded = (cnt + block_size - 1) / block_size * block_size;
+    for (int b = 0; b < padded / block_size; ++b) expert_ids[blk + b] = e;
+    pos += padded;
+    blk += padded / block_size;
+  }
+  return pos;
+}
+
+/* top-k of softmax(gating) per row, ties to the lower index; weights are the softmax probabilities (double
+ * arithmetic, rounded to float once). */
+void oracle_topk_softmax(const float* gating, int M, int E, int topk, float* weights, int32_t* ids) {
+  for (int m = 0; m < M; ++m) {
+    const float* g = gating + (size_t)m * E;
+    double mx = g[0], sum = 0.0;
+    for (int e = 1; e < E; ++e) mx = g[e] > mx ? g[e] : mx;
+    for (int e = 0; e < E; ++e) sum += exp((double)g[e] - mx);
+    for (int k = 0; k < topk; ++k) {
+      int best = -1;
+      for (int e = 0; e < E; ++e) {
+        int taken = 0;
+        for (int j = 0; j < k; ++j) taken |= ids[(size_t)m * topk + j] == e;
+        if (taken) continue;
+        if (best < 0 || g[e] > g[best]) best = e;
+      }
+      ids[(size_t)m * topk + k] = best;
+      weights[(size_t)m * topk + k] = (float)(exp((double)g[best] - mx) / sum);
+    }
+  }
+}

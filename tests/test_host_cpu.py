@@ -215,3 +215,25 @@ def test_moe_argument_validation_without_gpu(built):
     assert lib.b200awq_grouped_gemm_forward(None, 1, *p8, 1, 2, 32, 8, 4096, 4095, 128, 0, 16, *tail) == 1  # N % 8 != 0
     assert lib.b200awq_grouped_gemm_forward(None, 3, *p8, 1, 2, 32, 8, 4096, 4096, 128, 0, 16, *tail) == 1  # rows/token
     assert lib.b200awq_grouped_gemm_forward(None, 1, *p8, 1, 2, 32, 8, 4096, 4096, 128, 0, 16, *tail) == 1  # null pointers
+
+
+def test_c_oracle_moe_routing_matches_numpy_oracle(built):
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "libawqoracle.so"))
+    rng = np.random.default_rng(3)
+    for T, topk, E, block in [(4, 3, 5, 4), (1, 2, 8, 16), (50, 2, 8, 16), (9, 4, 16, 8)]:
+        ids = np.stack([rng.permutation(E)[:topk] for _ in range(T)]).astype(np.int32)
+        numel = ids.size
+        s = np.empty(numel + E * (block - 1), dtype=np.int32)
+        e = np.empty(numel + E, dtype=np.int32)
+        n = lib.oracle_moe_align_block_size(ids.ctypes.data_as(ctypes.c_void_p), numel, E, block,
+                                            s.ctypes.data_as(ctypes.c_void_p), e.ctypes.data_as(ctypes.c_void_p))
+        rs, re_, rn = O.moe_align_block_size(ids, block, E)
+        assert n == rn and np.array_equal(s, rs) and np.array_equal(e, re_)
+        g = (rng.standard_normal((T, E)) * 2).astype(np.float32)
+        w = np.empty((T, topk), dtype=np.float32)
+        i = np.empty((T, topk), dtype=np.int32)
+        lib.oracle_topk_softmax(g.ctypes.data_as(ctypes.c_void_p), T, E, topk, w.ctypes.data_as(ctypes.c_void_p),
+                                i.ctypes.data_as(ctypes.c_void_p))
+        rw, ri, _ = O.topk_softmax(g, topk)
+        assert np.array_equal(i, ri)
+        np.testing.assert_allclose(w, rw, rtol=1e-6, atol=1e-8)
