@@ -237,3 +237,23 @@ def test_c_oracle_moe_routing_matches_numpy_oracle(built):
         rw, ri, _ = O.topk_softmax(g, topk)
         assert np.array_equal(i, ri)
         np.testing.assert_allclose(w, rw, rtol=1e-6, atol=1e-8)
+
+
+def test_decode_program_recorder_refuses_cpu_tensors(built):
+    """No CPU path anywhere: the recorder raises on CPU tensors like the operators do."""
+    import torch
+
+    from autoawq_b200.program import DecodeProgram
+    from autoawq_b200.ext import B200AwqError
+
+    p = DecodeProgram()
+    x = torch.zeros((1, 64), dtype=torch.float16)
+    with pytest.raises(B200AwqError):
+        p.layernorm_forward_cuda(x, torch.ones(64, dtype=torch.float16), torch.empty_like(x), 1e-5)
+    with pytest.raises(B200AwqError):
+        p.gemm_forward_cuda(x, torch.zeros((64, 8), dtype=torch.int32), torch.zeros((1, 64), dtype=torch.float16),
+                            torch.zeros((1, 8), dtype=torch.int32), 8)
+    with pytest.raises(B200AwqError):
+        p.build()          # empty program
+    with pytest.raises(B200AwqError):
+        p.run()            # not built
