@@ -253,3 +253,33 @@ def test_program_llama8b_layer_shapes(api):
         prog.run()
     torch.cuda.synchronize()
     _check_against_oracle(blocks, bufs, "program 8B shapes")
+
+
+def test_program_bias_group64_and_older_source(api):
+    """Paths the Llama chain does not touch: linears with a bias (added before the fp16 rounding, as the per-op path
+    does), group size 64, and a linear whose source is the output of an op OLDER than its predecessor (read back from
+    global memory after that op's duty-warp stores, `ext_dep`)."""
+    from autoawq_b200.program import DecodeProgram
+
+    H, G = 2048, 64
+    rng = np.random.default_rng(5)
+    cs = [O.make_case(H, H, G, seed=70 + i) for i in range(3)]
+    sc = [(c["scales"].astype(np.float32) / (6.1 * 0.0108 * np.sqrt(H))).astype(np.float16) for c in cs]
+    ws = [O.dequantize_gemm(c["qweight"], c["qzeros"], s, G) for c, s in zip(cs, sc)]
+    bias = [(rng.standard_normal(H) * 0.25).astype(np.float16) for _ in range(3)]
+    x = _h0(H, 1, seed=17)
+    prog = DecodeProgram()
+    y0 = prog.gemm_forward_cuda(x, _t(cs[0]["qweight"]), _t(sc[0]), _t(cs[0]["qzeros"]), 8, bias=_t(bias[0]))
+    y1 = prog.gemm_forward_cuda(y0, _t(cs[1]["qweight"]), _t(sc[1]), _t(cs[1]["qzeros"]), 8, bias=_t(bias[1]))
+    y2 = prog.gemm_forward_cuda(y0, _t(cs[2]["qweight"]), _t(sc[2]), _t(cs[2]["qzeros"]), 8, bias=_t(bias[2]))  # older src
+    prog.build()
+    assert prog.fused and prog.kernel_ops == 3
+    for _ in range(3):
+        prog.run()
+    torch.cuda.synchronize()
+    _no_abort("bias / g64 / ext_dep")
+    xin = [x.cpu().numpy(), y0.cpu().numpy(), y0.cpu().numpy()]
+    for i, y in enumerate((y0, y1, y2)):
+        ref = O.gemm_f64(xin[i], ws[i]) + bias[i].astype(np.float64)
+        budget = np.abs(xin[i].astype(np.float64)) @ np.abs(ws[i].astype(np.float64))
+        _close(y.cpu().numpy(), ref, budget, f"op {i}")
