@@ -88,6 +88,7 @@ def _experts(E, K, N, G, seed):
 
 @pytest.mark.parametrize("T,topk,E,K,N,G,kernel", [
     (1, 2, 8, 1024, 512, 128, "ring"), (5, 2, 8, 1024, 512, 128, "ring"), (37, 2, 4, 512, 256, 64, "ring"),
+    (2, 2, 8, 1024, 512, 128, "ring"), (3, 2, 8, 1024, 512, 128, "ring"),   # the 2- and 4-slot variants of the ring kernel
     (3, 3, 6, 1536, 96, 128, "staged"),            # N not a multiple of 256: the register-staged kernel
     (5, 2, 8, 1024, 512, 128, "staged-forced"),    # knob 12 = 2
 ])
