@@ -1,0 +1,28 @@
+"""Resource budget of the decode-program kernel, checked from ptxas on the CPU box (nvcc cross-compiles sm_100a here):
+one CTA of 320 threads per SM must fit the register file (65536 / 320 = 204 registers per thread) without spilling -
+a spill in the tile loop, or a register count that drops the launch to zero resident CTAs, would only show up on the
+GPU otherwise."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="needs nvcc")
+def test_program_kernel_register_and_spill_budget(tmp_path):
+    src = os.path.join(ROOT, "autoawq_b200", "csrc", "program.cu")
+    out = subprocess.run(
+        ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xptxas", "-v", "-c", src,
+         "-o", str(tmp_path / "program.o")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    log = out.stderr + out.stdout
+    entries = re.findall(r"Compiling entry function '(\S*program_kernel\S*)'.*?\n.*?(\d+) bytes stack frame, (\d+) bytes "
+                         r"spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", log)
+    assert len(entries) == 2, log[-1500:]          # program_kernel<1>, program_kernel<2>
+    for name, stack, st, ld, regs in entries:
+        assert int(st) == 0 and int(ld) == 0 and int(stack) == 0, f"{name}: spills"
+        assert int(regs) <= 204, f"{name}: {regs} registers x 320 threads exceed the register file"
