@@ -20,8 +20,8 @@ def test_program_kernel_register_and_spill_budget(tmp_path):
          "-o", str(tmp_path / "program.o")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-2000:]
     log = out.stderr + out.stdout
-    entries = re.findall(r"Compiling entry function '(\S*program_kernel\S*)'.*?\n.*?(\d+) bytes stack frame, (\d+) bytes "
-                         r"spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", log)
+    entries = re.findall(r"Compiling entry function '(\S*program_kernel\S*)'[^\n]*\n[^\n]*\n\s*(\d+) bytes stack frame, "
+                         r"(\d+) bytes spill stores, (\d+) bytes spill loads\n[^\n]*Used (\d+) registers", log)
     assert len(entries) == 2, log[-1500:]          # program_kernel<1>, program_kernel<2>
     for name, stack, st, ld, regs in entries:
         assert int(st) == 0 and int(ld) == 0 and int(stack) == 0, f"{name}: spills"
