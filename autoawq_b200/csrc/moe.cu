@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(128)
   extern __shared__ float ts_smem[];   // [4 warps][E]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * 4 + warp;
+  pdl_wait();      // the gating logits come from the predecessor kernel (PDL launches may start early)
+  pdl_trigger();
   if (m >= M) return;
   float* p = ts_smem + (size_t)warp * E;
   const float* g = gating + (int64_t)m * E;
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(128)
       topk_w[(int64_t)m * topk + k] = best * inv;
       topk_ids[(int64_t)m * topk + k] = bi;
       src_rows[(int64_t)m * topk + k] = k * M + m;
-      p[bi] = -2.f;   // taken
+      if (bi < E) p[bi] = -2.f;   // taken (a row of NaNs selects nothing: bi stays at its sentinel)
     }
     __syncwarp();
   }
@@ -75,8 +77,14 @@ __global__ void __launch_bounds__(128)
 cudaError_t topk_softmax(const float* gating, float* topk_w, int* topk_ids, int* src_rows, int M, int E, int topk,
                          cudaStream_t st) {
   if (M == 0) return cudaSuccess;
-  return launch_kernel(topk_softmax_kernel, dim3((M + 3) / 4), dim3(128), (size_t)4 * E * sizeof(float), st, gating,
-                       topk_w, topk_ids, src_rows, M, E, topk);
+  const size_t smem = (size_t)4 * E * sizeof(float);
+  if (smem > (size_t)200 * 1024) return cudaErrorNotSupported;
+  if (smem > (size_t)48 * 1024) {   // beyond the default dynamic shared memory limit (E > 3072)
+    cudaError_t e = cudaFuncSetAttribute(topk_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  return launch_kernel(topk_softmax_kernel, dim3((M + 3) / 4), dim3(128), smem, st, gating, topk_w, topk_ids, src_rows,
+                       M, E, topk);
 }
 
 // ------------------------------------------------------------------------------------ moe_align_block_size
@@ -87,6 +95,8 @@ __global__ void __launch_bounds__(1024)
                      int* __restrict__ sorted_ids, int* __restrict__ expert_ids, int* __restrict__ num_post_pad) {
   extern __shared__ int ma_smem[];   // [E] padded counts -> run offsets
   const int e = threadIdx.x;
+  pdl_wait();      // topk_ids are written by the predecessor (topk_softmax)
+  pdl_trigger();
   int cnt = 0;
   if (e < num_experts)
     for (int i = 0; i < numel; ++i) cnt += (topk_ids[i] == e);
@@ -132,6 +142,8 @@ __global__ void __launch_bounds__(kGvWarps * 32, 2)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tig = lane & 3;
   const int hb = blockIdx.y;                       // half-block: sorted slots hb*8 .. hb*8+7
+  pdl_wait();      // routing data and activations come from predecessor kernels; nothing is read before this
+  pdl_trigger();
   if (hb * MT >= *num_post_pad) return;
   if (tid < MT) {
     const int id = sorted_ids[hb * MT + tid];

@@ -24,6 +24,8 @@ from .shard import PackedGemm, _bounds
 # which way a linear is split, by the last component of its name (Llama / Mistral / Mixtral / Qwen naming)
 COLUMN_PARALLEL = ("q_proj", "k_proj", "v_proj", "gate_proj", "up_proj", "w1", "w3", "qkv_proj", "gate_up_proj")
 ROW_PARALLEL = ("o_proj", "down_proj", "w2", "dense", "out_proj")
+# (the fused names qkv_proj / gate_up_proj are split PER SECTION, see column_sections: one contiguous N range would
+# leave rank 0 with q heads only / gate columns only)
 
 
 class CheckpointIndex:
@@ -86,11 +88,48 @@ def _read(index: CheckpointIndex, name: str, device, rows: Optional[slice] = Non
     return t.contiguous().to(device, non_blocking=False)
 
 
+def column_sections(prefix: str, N: int, sections=None, qkv_heads=None):
+    """[(start, width, quantum or None)] of a column-parallel tensor.  Plain projections are one section; the fused
+    names need their section widths: gate_up_proj = two halves; qkv_proj = (n_heads, n_kv_heads, head_dim) ->
+    q | k | v split by head (quantum = head_dim so attention stays local, as shard.shard_qkv does)."""
+    leaf = prefix.rsplit(".", 1)[-1]
+    if sections is not None:
+        out, base = [], 0
+        for w in sections:
+            out.append((base, int(w), None))
+            base += int(w)
+        if base != N:
+            raise ValueError(f"{prefix}: sections {list(sections)} do not add up to N = {N}")
+        return out
+    if leaf == "gate_up_proj":
+        if N % 2:
+            raise ValueError(f"{prefix}: odd width {N} cannot be [gate | up]")
+        return [(0, N // 2, None), (N // 2, N // 2, None)]
+    if leaf == "qkv_proj":
+        if qkv_heads is None:
+            raise ValueError(f"{prefix}: a fused qkv tensor needs qkv_heads=(n_heads, n_kv_heads, head_dim) to be "
+                             "split by head; a contiguous column range would give a rank q heads only")
+        h, hkv, d = qkv_heads
+        if (h + 2 * hkv) * d != N:
+            raise ValueError(f"{prefix}: qkv_heads {qkv_heads} do not match N = {N}")
+        return [(0, h * d, d), (h * d, hkv * d, d), ((h + hkv) * d, hkv * d, d)]
+    return [(0, N, None)]
+
+
 def load_packed_linear(index: CheckpointIndex, prefix: str, device, tp_rank: int = 0, tp_world: int = 1,
-                       mode: Optional[str] = None, column_quantum: int = 8) -> PackedGemm:
-    """One packed linear, or this rank's shard of it.  mode: "column" (split N on `column_quantum`-column boundaries),
-    "row" (split K on group boundaries; the bias stays on rank 0 so the all-reduce adds it once), "replicate",
-    or None = by name (`split_mode`)."""
+                       mode: Optional[str] = None, column_quantum: Optional[int] = None, sections=None,
+                       qkv_heads=None) -> PackedGemm:
+    """One packed linear, or this rank's shard of it.  mode: "column" (split N), "row" (split K on group
+    boundaries; the bias stays on rank 0 so the all-reduce adds it once), "replicate", or None = by name
+    (`split_mode`).
+
+    Column quantum: a column-parallel linear feeds a row-parallel one (gate/up -> down, q/k/v -> attention -> o)
+    whose K is split on ITS group boundaries, so the producer's columns must be split on the same boundaries or
+    the shards do not line up whenever (N / G) % tp_world != 0 (e.g. I = 11008, G = 128, tp = 4: columns from
+    2752 but rows from 2688).  Default = this linear's own group size (the model-wide q_group_size,
+    awq/models/_config.py:12), never less than one packed word (8); k_proj / v_proj feed attention, not a
+    row-parallel K split, and default to one packed word (pass head_dim to keep heads whole); pass the consumer's
+    group size / head_dim when they differ.  Fused tensors are split per section (`column_sections`)."""
     from safetensors import safe_open
 
     mode = mode or split_mode(prefix)
@@ -105,14 +144,22 @@ def load_packed_linear(index: CheckpointIndex, prefix: str, device, tp_rank: int
     G = K // KG
     has_bias = prefix + ".bias" in index.files
     if mode == "column":
-        if column_quantum % 8 != 0:
-            raise ValueError("column quantum must be a multiple of 8 (one packed word)")
-        n0, n1 = _bounds(N, tp_rank, tp_world, column_quantum)
-        cw = slice(n0 // 8, n1 // 8)
-        return PackedGemm(_read(index, prefix + ".qweight", device, cols=cw),
-                          _read(index, prefix + ".qzeros", device, cols=cw),
-                          _read(index, prefix + ".scales", device, cols=slice(n0, n1)),
-                          _read(index, prefix + ".bias", device, cols=slice(n0, n1)) if has_bias else None)
+        parts = []
+        for base, width, q in column_sections(prefix, N, sections, qkv_heads):
+            kv = prefix.rsplit(".", 1)[-1] in ("k_proj", "v_proj")
+            quantum = column_quantum if column_quantum is not None else (q if q is not None else (8 if kv else max(8, G)))
+            if quantum % 8 != 0:
+                raise ValueError("column quantum must be a multiple of 8 (one packed word)")
+            if width % quantum != 0:
+                raise ValueError(f"{prefix}: section width {width} is not a multiple of the column quantum {quantum}")
+            n0, n1 = _bounds(width, tp_rank, tp_world, quantum)
+            n0, n1 = base + n0, base + n1
+            cw = slice(n0 // 8, n1 // 8)
+            parts.append(PackedGemm(_read(index, prefix + ".qweight", device, cols=cw),
+                                    _read(index, prefix + ".qzeros", device, cols=cw),
+                                    _read(index, prefix + ".scales", device, cols=slice(n0, n1)),
+                                    _read(index, prefix + ".bias", device, cols=slice(n0, n1)) if has_bias else None))
+        return parts[0] if len(parts) == 1 else fuse_columns(parts)
     if mode == "row":
         k0, k1 = _bounds(K, tp_rank, tp_world, G)
         return PackedGemm(_read(index, prefix + ".qweight", device, rows=slice(k0, k1)),
@@ -127,13 +174,39 @@ def load_packed_linear(index: CheckpointIndex, prefix: str, device, tp_rank: int
 
 
 def load_packed_linears(path: str, device, tp_rank: int = 0, tp_world: int = 1, prefixes: Optional[Iterable[str]] = None,
-                        column_quantum: int = 8) -> Dict[str, PackedGemm]:
-    """Every packed linear of a checkpoint directory (or the given prefixes), sharded for (tp_rank, tp_world)."""
+                        column_quantum: Optional[int] = None, qkv_heads=None) -> Dict[str, PackedGemm]:
+    """Every packed linear of a checkpoint directory (or the given prefixes), sharded for (tp_rank, tp_world).
+    q/k/v projections (and a fused qkv_proj) are split by head when `qkv_heads=(n_heads, n_kv_heads, head_dim)` is
+    given; everything column-parallel otherwise on group boundaries (see load_packed_linear)."""
     index = CheckpointIndex(path)
     out = {}
     for p in (list(prefixes) if prefixes is not None else index.linear_prefixes()):
-        out[p] = load_packed_linear(index, p, device, tp_rank, tp_world, None, column_quantum)
+        cq = column_quantum
+        if cq is None and qkv_heads is not None and p.rsplit(".", 1)[-1] in ("q_proj", "k_proj", "v_proj"):
+            cq = qkv_heads[2]
+        out[p] = load_packed_linear(index, p, device, tp_rank, tp_world, None, cq, qkv_heads=qkv_heads)
+    check_tp_alignment(out, tp_rank, tp_world)
     return out
+
+
+def check_tp_alignment(shards: Dict[str, PackedGemm], tp_rank: int, tp_world: int) -> None:
+    """Column-parallel producers and the row-parallel consumer of the same block must hold matching widths on every
+    rank: gate/up (w1/w3) columns == down (w2) rows.  Raises instead of letting a caller pair the wrong channels."""
+    if tp_world == 1:
+        return
+    by_parent: Dict[str, Dict[str, PackedGemm]] = {}
+    for name, p in shards.items():
+        parent, leaf = name.rsplit(".", 1) if "." in name else ("", name)
+        by_parent.setdefault(parent, {})[leaf] = p
+    for parent, d in by_parent.items():
+        for prods, cons in ((("gate_proj", "up_proj"), "down_proj"), (("w1", "w3"), "w2")):
+            if cons in d:
+                for pr in prods:
+                    if pr in d and d[pr].out_features != d[cons].in_features:
+                        raise ValueError(f"{parent}: rank {tp_rank}/{tp_world} holds {d[pr].out_features} columns of {pr} "
+                                         f"but {d[cons].in_features} rows of {cons}; split both on the same boundaries")
+        if "gate_up_proj" in d and "down_proj" in d and d["gate_up_proj"].out_features != 2 * d["down_proj"].in_features:
+            raise ValueError(f"{parent}: gate_up_proj / down_proj shards do not line up on rank {tp_rank}")
 
 
 def fuse_columns(parts: Iterable[PackedGemm]) -> PackedGemm:

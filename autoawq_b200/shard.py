@@ -113,24 +113,35 @@ def all_reduce_sum(y: torch.Tensor, group=None) -> torch.Tensor:
 
 class TensorParallelMLP:
     """gate|up (column-parallel, fused) -> SiLU*mul -> down (row-parallel) -> all-reduce, on the B200 kernels.
-    Per-rank weights are the slices above; used by the 70B-shape multi-GPU bench and tests."""
+    Per-rank weights are the slices above; used by the 70B-shape tensor-parallel bench leg (bench.py `tp70b`) and
+    the tests.  gate / up are split on the boundaries of down's K split (its group size), so the activation width
+    of a rank always equals its number of down rows, also when (I / G) % world != 0."""
 
     def __init__(self, gate: PackedGemm, up: PackedGemm, down: PackedGemm, rank: int, world: int, group=None):
         from . import ext
 
         self.ext, self.group = ext, group
-        g, u = shard_columns(gate, rank, world, 128), shard_columns(up, rank, world, 128)
+        quantum = max(8, down.group_size)
+        g, u = shard_columns(gate, rank, world, quantum), shard_columns(up, rank, world, quantum)
+        bias = None
+        if g.bias is not None or u.bias is not None:
+            z = lambda p: p.bias if p.bias is not None else torch.zeros(  # noqa: E731
+                p.out_features, dtype=torch.float16, device=p.qweight.device)
+            bias = torch.cat([z(g), z(u)]).contiguous()
         self.gu = PackedGemm(torch.cat([g.qweight, u.qweight], 1).contiguous(),
                              torch.cat([g.qzeros, u.qzeros], 1).contiguous(),
-                             torch.cat([g.scales, u.scales], 1).contiguous())
+                             torch.cat([g.scales, u.scales], 1).contiguous(), bias)
         self.down = shard_rows(down, rank, world)
-        self.G = gate.group_size
+        if g.out_features != self.down.in_features or u.out_features != self.down.in_features:
+            raise ValueError(f"rank {rank}/{world}: gate/up shard width {g.out_features}/{u.out_features} != down shard "
+                             f"rows {self.down.in_features}")
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         e = self.ext
-        gu = e.linear_forward("gemm", x, self.gu.qweight, self.gu.scales, self.gu.qzeros, self.G)
+        gu = e.linear_forward("gemm", x, self.gu.qweight, self.gu.scales, self.gu.qzeros, self.gu.group_size,
+                              self.gu.bias)
         act = torch.empty((gu.shape[0], gu.shape[1] // 2), dtype=torch.float16, device=gu.device)
         e.silu_and_mul(act, gu)
-        y = e.linear_forward("gemm", act, self.down.qweight, self.down.scales, self.down.qzeros, self.G,
+        y = e.linear_forward("gemm", act, self.down.qweight, self.down.scales, self.down.qzeros, self.down.group_size,
                              self.down.bias)
         return all_reduce_sum(y, self.group)

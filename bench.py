@@ -232,6 +232,153 @@ def cpu_reference_sample(M, layers_sample, reps, threads=None):
     return min(ts), cores
 
 
+
+# ------------------------------------------------------------------- same-box GPU reference (Triton) leg
+def _load_reference_triton():
+    """The reference's own in-tree GPU kernels (awq/modules/triton/gemm.py: awq_gemm_triton :310-359,
+    awq_dequantize_triton :255-302), loaded BY FILE from the unmodified copy in baseline/_ref (installed by
+    __graft_entry__.build(); the file needs only torch + triton).  Measurement infrastructure: nothing of it is
+    on the product path."""
+    import importlib.util
+
+    for base in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        f = os.path.join(base, "awq", "modules", "triton", "gemm.py")
+        if os.path.isfile(f):
+            spec = importlib.util.spec_from_file_location("ref_triton_gemm", f)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            return mod
+    return None
+
+
+def triton_reference_leg(torch, rep, M, steps, warmup):
+    """What the unmodified reference runs on this box when `awq_ext` is absent (awq/modules/linear/gemm.py:60-69):
+    decode -> awq_gemm_triton(x, qweight, scales, qzeros, split_k_iters=8) per linear; prefill (B*S >= 1024) ->
+    awq_dequantize_triton + torch.matmul.  Same packed tensors as our arm, CUDA events, graph replay when the
+    launches capture.  Also the max error of both arms against the fp64 oracle contraction on one linear
+    (our error must not exceed the reference's)."""
+    T = _load_reference_triton()
+    if T is None:
+        return {"unavailable": "no copy of the reference on this box (baseline/_ref missing)"}
+    out = {"source": "awq/modules/triton/gemm.py (unmodified, baseline/_ref)",
+           "path": "awq_gemm_triton split_k=8" if M * 1 < 1024 else "awq_dequantize_triton + torch.matmul"}
+    xk = {HIDDEN: rep.xn, INTER: rep.act}
+
+    def lin(K, w):
+        x = xk[K]
+        if M >= 1024:   # gemm.py:61-65
+            return torch.matmul(x, T.awq_dequantize_triton(w[0], w[1], w[2]))
+        return T.awq_gemm_triton(x, w[0], w[1], w[2], 8)
+
+    def step():
+        for lw in rep.w:
+            for name, K, _N in LINEARS:
+                lin(K, lw[name])
+
+    try:
+        step()   # JIT
+        torch.cuda.synchronize()
+    except Exception as ex:  # noqa: BLE001
+        return {"unavailable": f"reference Triton path failed on this box: {type(ex).__name__}: {str(ex)[:160]}"}
+    fn, graphed = step, False
+    try:
+        g, _ = capture(torch, step)
+        fn, graphed = g.replay, True
+    except Exception:  # noqa: BLE001
+        torch.cuda.synchronize()
+    sec = timed(torch, fn, steps, warmup)
+    out.update({"tok_s": round(M * steps / sec, 2), "ms_per_step": round(sec / steps * 1e3, 4), "cuda_graph": graphed,
+                "launch_note": "linears only (128 per step), no glue kernels"})
+    per = {}
+    for name, K, _N in LINEARS:
+        def shape_step(name=name, K=K):
+            for lw in rep.w:
+                lin(K, lw[name])
+        try:
+            gs, _ = capture(torch, shape_step)
+            f2 = gs.replay
+        except Exception:  # noqa: BLE001
+            f2 = shape_step
+        t = timed(torch, f2, max(3, steps // 3), 2)
+        per[name] = round(t / max(3, steps // 3) / len(rep.w) * 1e6, 2)
+    out["per_linear_us"] = per
+    # error of both arms vs the fp64 oracle on layer 0's o-projection (4096 x 4096), at most 64 tokens
+    try:
+        import numpy as np
+
+        from oracle import awq_oracle as O
+
+        qw, sc, qz = rep.w[0]["o"]
+        w64 = O.dequantize_gemm(qw.cpu().numpy(), qz.cpu().numpy(), sc.cpu().numpy(), GROUP).astype(np.float64)
+        xm = rep.xn[: min(M, 64)].contiguous()
+        ref = xm.cpu().numpy().astype(np.float64) @ w64
+        rms = float(np.sqrt(np.mean(ref**2))) or 1.0
+        y_t = (torch.matmul(xm, T.awq_dequantize_triton(qw, sc, qz)) if M >= 1024
+               else T.awq_gemm_triton(xm, qw, sc, qz, 8)).float().cpu().numpy()
+        y_o = rep.lin(xm, (qw, sc, qz)).float().cpu().numpy()
+        out["max_err_over_rms"] = {"reference_triton": float(np.abs(y_t - ref).max() / rms),
+                                   "ours": float(np.abs(y_o - ref).max() / rms),
+                                   "on": f"o_proj 4096x4096 layer 0, {xm.shape[0]} token(s), fp64 oracle contraction"}
+    except Exception as ex:  # noqa: BLE001
+        out["max_err_over_rms"] = {"error": str(ex)[:160]}
+    return out
+
+
+def gemv_4096_leg(torch, ext, dev, steps, peaks):
+    """The metric's own shape: ONE 4096 x 4096 g128 GEMV (M = 1), stand-alone launches rotating over a pool of
+    distinct weights larger than L2 (48 x 8.7 MB = 419 MB), CUDA graph of the pool, CUDA events."""
+    K = N = HIDDEN
+    pool = 48
+    g = torch.Generator(device=dev).manual_seed(123)
+    ws = []
+    for _ in range(pool):
+        qw = torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, device=dev, generator=g)
+        qz = torch.randint(-2**31, 2**31 - 1, (K // GROUP, N // 8), dtype=torch.int32, device=dev, generator=g)
+        s = ((torch.rand((K // GROUP, N), device=dev, generator=g) * 0.5 + 0.75) / (6.1 * K**0.5)).half()
+        ws.append((qw, s, qz))
+    x = torch.randn((1, K), device=dev, dtype=torch.float16, generator=g)
+
+    def sweep():
+        for w in ws:
+            ext.gemm_forward_cuda(x, w[0], w[1], w[2], 8)
+
+    gr, _ = capture(torch, sweep)
+    n = max(5, steps)
+    sec = timed(torch, gr.replay, n, 3)
+    us = sec / n / pool * 1e6
+    b = linear_bytes(K, N, 1)
+    return {"shape": "4096x4096 g128 M=1", "us_per_launch": round(us, 3), "gbs": round(b / us / 1e3, 1),
+            "frac": round(b / us / 1e3 / peaks["hbm_gbs"], 4), "alg_bytes": b,
+            "pool": f"{pool} distinct weight sets ({pool * b / 1e6:.0f} MB > L2), one CUDA graph of {pool} launches"}
+
+
+def prefill_leg(torch, rep_weights, dev, steps, peaks):
+    """BASELINE config 3 as a secondary leg of the default run: bs=1, seq=4096 through every quantised linear
+    (tcgen05 kernel), same weights; tok/s, TFLOP/s, fraction of the sustained bf16 peak."""
+    M = 4096
+    from autoawq_b200 import ext
+
+    xn = torch.randn((M, HIDDEN), device=dev, dtype=torch.float16) * 0.5
+    act = torch.randn((M, INTER), device=dev, dtype=torch.float16) * 0.5
+    xk = {HIDDEN: xn, INTER: act}
+
+    def step():
+        for lw in rep_weights:
+            for name, K, _N in LINEARS:
+                w = lw[name]
+                ext.gemm_forward_cuda(xk[K], w[0], w[1], w[2], 8)
+
+    gr, _ = capture(torch, step)
+    n = max(3, min(steps, 6))
+    sec = timed(torch, gr.replay, n, 3)
+    flops = sum(2.0 * M * K * N for _, K, N in LINEARS) * len(rep_weights)
+    tf = flops / (sec / n) / 1e12
+    return {"workload": "Llama-3-8B prefill bs=1 seq=4096, quantised linears (128 launches)", "tok_s": round(M * n / sec, 1),
+            "ms_per_step": round(sec / n * 1e3, 3), "tflops": round(tf, 1),
+            "frac_of_sustained_bf16_peak": round(tf / peaks["bf16_tflops_sustained"], 4),
+            "frac_of_burst_bf16_peak": round(tf / peaks["bf16_tflops"], 4), "kernel": "gemm_tc_kernel (tcgen05)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,6 +393,9 @@ def main():
                     help="decode: 1 = record the step once and run it as ONE persistent kernel (b200awq_program_*); "
                          "0 = one kernel launch per operator call")
     ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: fewer layers => INVALID as a bench value")
+    ap.add_argument("--legs", type=int, default=1,
+                    help="1: also run the secondary legs at N=1 (reference Triton on the same box, 4096x4096 GEMV, "
+                         "prefill); 0: headline only")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -297,7 +447,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
     dist = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # NCCL's INFO log (communicator ranks, NVLS / ring choice) goes to STDERR: stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
@@ -425,6 +578,15 @@ def main():
     n_eager = max(3, a.steps // 5)
     sec_eager = timed(torch, eager_step, n_eager, 2, dist)
 
+    # secondary legs (N = 1 only; the headline metric is unchanged): the reference's Triton kernels on the same box,
+    # the metric's own 4096 x 4096 GEMV, and config 3 (prefill) - all CUDA-event timed like the value leg
+    if world == 1 and a.legs:
+        config["triton_reference"] = triton_reference_leg(torch, rep, M, max(5, a.steps // 2), 3)
+        if a.mode == "decode":
+            config["gemv_4096"] = gemv_4096_leg(torch, rep.ext, dev, a.steps, peaks)
+            eager_ops = timed(torch, lambda: rep.step(rep.h), max(3, a.steps // 5), 2)
+            config["per_op_eager_tok_s"] = round(max(3, a.steps // 5) / eager_ops, 1)
+            config["prefill"] = prefill_leg(torch, rep.w, dev, a.steps, peaks)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

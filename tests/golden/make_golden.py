@@ -48,6 +48,12 @@ def _import_reference():
             load_checkpoint_and_dispatch=lambda *a, **k: None,
         ),
     )
+    # The repo root is on sys.path (for oracle.*) and holds THIS repo's `awq_ext` / `awq_v2_ext` drop-in packages:
+    # the reference would bind them at import (awq/utils/module.py:4-9) and its forward would then run on our CUDA
+    # extension instead of its own naive CPU branch.  Goldens must come from the reference alone: mask both names
+    # (a None entry makes the import raise, try_import returns None).
+    sys.modules["awq_ext"] = None
+    sys.modules["awq_v2_ext"] = None
     sys.path.insert(0, REF)
     import awq  # noqa: F401
     import awq.modules.linear.gemm as G

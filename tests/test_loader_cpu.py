@@ -104,3 +104,83 @@ def test_shards_match_shard_py_and_recompose(ckpt, world):
     r, world2 = 1, 2
     qkv = fuse_columns(load_packed_linear(idx, f"model.layers.0.self_attn.{n}_proj", "cpu", r, world2) for n in "qkv")
     assert qkv.out_features == (256 + 64 + 64) // world2 and qkv.bias is not None and qkv.bias.shape[0] == qkv.out_features
+
+
+def test_uneven_groups_column_and_row_shards_line_up(tmp_path):
+    """I = 11008, G = 128, tp = 4 -> 86 groups do not divide by 4.  gate / up columns must be split on
+    the boundaries of down's K split, or a rank's activation width differs from its down rows."""
+    from safetensors.torch import save_file
+
+    from autoawq_b200 import shard
+    from autoawq_b200.loader import check_tp_alignment, load_packed_linears
+
+    H, I, G, world = 128, 11008, 128, 4
+    tensors = {}
+    for i, (name, (K, N)) in enumerate({"mlp.gate_proj": (H, I), "mlp.up_proj": (H, I), "mlp.down_proj": (I, H)}.items()):
+        rng = np.random.default_rng(i)
+        p = f"model.layers.0.{name}"
+        tensors[p + ".qweight"] = torch.from_numpy(rng.integers(-2**31, 2**31 - 1, (K, N // 8), dtype=np.int64).astype(np.int32))
+        tensors[p + ".qzeros"] = torch.from_numpy(rng.integers(-2**31, 2**31 - 1, (K // G, N // 8), dtype=np.int64).astype(np.int32))
+        tensors[p + ".scales"] = torch.from_numpy(rng.random((K // G, N)).astype(np.float16))
+    save_file(tensors, str(tmp_path / "model.safetensors"))
+    widths = []
+    for r in range(world):
+        sh = load_packed_linears(str(tmp_path), "cpu", r, world)     # check_tp_alignment runs inside
+        g, u, d = (sh[f"model.layers.0.mlp.{n}_proj"] for n in ("gate", "up", "down"))
+        assert g.out_features == u.out_features == d.in_features
+        k0, k1 = shard._bounds(I, r, world, G)
+        assert torch.equal(g.qweight, tensors["model.layers.0.mlp.gate_proj.qweight"][:, k0 // 8:k1 // 8])
+        assert torch.equal(d.qweight, tensors["model.layers.0.mlp.down_proj.qweight"][k0:k1])
+        widths.append(d.in_features)
+    assert sum(widths) == I and len(set(widths)) == 2           # 21 / 22 groups: genuinely uneven
+    # the old behaviour (8-column quantum for gate / up) is caught, not silently mis-paired
+    bad = load_packed_linears(str(tmp_path), "cpu", 1, world, column_quantum=8,
+                              prefixes=["model.layers.0.mlp.gate_proj", "model.layers.0.mlp.up_proj"])
+    bad["model.layers.0.mlp.down_proj"] = load_packed_linears(
+        str(tmp_path), "cpu", 1, world, prefixes=["model.layers.0.mlp.down_proj"])["model.layers.0.mlp.down_proj"]
+    with pytest.raises(ValueError):
+        check_tp_alignment(bad, 1, world)
+    # TensorParallelMLP uses the same boundaries (and carries gate / up biases)
+    whole = {n: shard.PackedGemm(tensors[f"model.layers.0.mlp.{n}_proj.qweight"], tensors[f"model.layers.0.mlp.{n}_proj.qzeros"],
+                                 tensors[f"model.layers.0.mlp.{n}_proj.scales"]) for n in ("gate", "up", "down")}
+    whole["gate"].bias = torch.arange(I, dtype=torch.float16)
+    try:
+        mlp = shard.TensorParallelMLP(whole["gate"], whole["up"], whole["down"], 1, world)
+    except ImportError:
+        pytest.skip("libb200awq.so not built")
+    assert mlp.gu.out_features == 2 * mlp.down.in_features
+    k0, k1 = shard._bounds(I, 1, world, G)
+    assert torch.equal(mlp.gu.bias[: k1 - k0], whole["gate"].bias[k0:k1]) and float(mlp.gu.bias[k1 - k0:].abs().sum()) == 0
+
+
+def test_fused_names_are_split_per_section(tmp_path):
+    """qkv_proj / gate_up_proj (Phi-3-style fused checkpoints) must be split per section, not as one
+    contiguous N range."""
+    from safetensors.torch import save_file
+
+    from autoawq_b200 import shard
+    from autoawq_b200.loader import CheckpointIndex, load_packed_linear
+
+    H, I, G, heads, kv, d = 256, 512, 64, 4, 2, 64
+    tensors = {}
+    for i, (name, (K, N)) in enumerate({"self_attn.qkv_proj": (H, (heads + 2 * kv) * d), "mlp.gate_up_proj": (H, 2 * I)}.items()):
+        c = O.make_case(K, N, G, seed=i)
+        p = f"model.layers.0.{name}"
+        tensors[p + ".qweight"], tensors[p + ".qzeros"], tensors[p + ".scales"] = (torch.from_numpy(c[k]) for k in
+                                                                                    ("qweight", "qzeros", "scales"))
+    save_file(tensors, str(tmp_path / "model.safetensors"))
+    idx = CheckpointIndex(str(tmp_path))
+    world = 2
+    for r in range(world):
+        gu = load_packed_linear(idx, "model.layers.0.mlp.gate_up_proj", "cpu", r, world)
+        whole = shard.PackedGemm(*(tensors[f"model.layers.0.mlp.gate_up_proj.{k}"] for k in ("qweight", "qzeros", "scales")))
+        half = I // world
+        assert gu.out_features == 2 * half
+        assert torch.equal(gu.scales[:, :half], whole.scales[:, r * half:(r + 1) * half])              # gate share
+        assert torch.equal(gu.scales[:, half:], whole.scales[:, I + r * half:I + (r + 1) * half])      # up share
+        qkv = load_packed_linear(idx, "model.layers.0.self_attn.qkv_proj", "cpu", r, world, qkv_heads=(heads, kv, d))
+        wq = shard.PackedGemm(*(tensors[f"model.layers.0.self_attn.qkv_proj.{k}"] for k in ("qweight", "qzeros", "scales")))
+        exp = shard.shard_qkv(wq, heads, kv, d, r, world)
+        assert torch.equal(qkv.qweight, exp.qweight) and torch.equal(qkv.scales, exp.scales)
+    with pytest.raises(ValueError):
+        load_packed_linear(idx, "model.layers.0.self_attn.qkv_proj", "cpu", 0, world)   # heads unknown: refuse
