@@ -71,6 +71,9 @@ SIGNATURES = {
     ),
     "b200awq_program_create": (_c_int, [ctypes.POINTER(Op), _c_int, ctypes.POINTER(_c_void_p)]),
     "b200awq_program_num_ops": (_c_int, [_c_void_p]),
+    "b200awq_program_kind": (_c_int, [_c_void_p]),
+    "b200awq_stream_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "b200awq_stream_pack": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p]),
     "b200awq_program_run": (_c_int, [_c_void_p, _c_void_p, _c_size_t, _c_void_p]),
     "b200awq_program_destroy": (_c_int, [_c_void_p]),
 }

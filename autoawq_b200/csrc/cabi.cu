@@ -177,9 +177,26 @@ int b200awq_program_num_ops(b200awq_program_t prog) {
   return prog == nullptr ? 0 : program_num_ops(reinterpret_cast<Program*>(prog));
 }
 
+int b200awq_program_kind(b200awq_program_t prog) {
+  return prog == nullptr ? 0 : (program_is_stream(reinterpret_cast<Program*>(prog)) ? 2 : 1);
+}
+
+size_t b200awq_stream_bytes(int K, int N, int group_size) {
+  return stream_format_supported(K, N, group_size, 0) ? stream_format_bytes(K, N, group_size) : 0;
+}
+
+int b200awq_stream_pack(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out, int K, int N,
+                        int group_size, int mode, b200awq_stream_t stream) {
+  if (!qweight || !scales || !qzeros || !out) return B200AWQ_EINVAL;
+  if (!shape_ok(1, K, N, group_size)) return B200AWQ_EINVAL;
+  if (!stream_format_supported(K, N, group_size, mode)) return B200AWQ_EUNSUPPORTED;
+  return fold(stream_pack(qweight, scales, qzeros, out, K, N, group_size, mode, static_cast<cudaStream_t>(stream)));
+}
+
 int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
   if (prog == nullptr) return B200AWQ_EINVAL;
   Program* p = reinterpret_cast<Program*>(prog);
+  if (program_is_stream(p)) return fold(program_run(p, nullptr, static_cast<cudaStream_t>(stream)));   // owns its rows
   Ws ws;
   // four rows of 64-bit packed sums (= 8 floats per column), max-N columns rounded up to 8, rotate through the ops
   if (!carve(workspace, workspace_bytes, 8, (program_max_n(p) + 7) & ~7, &ws)) return B200AWQ_EWORKSPACE;

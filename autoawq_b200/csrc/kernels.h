@@ -83,6 +83,13 @@ int program_max_n(const Program* p);
 int program_m(const Program* p);
 int program_num_ops(const Program* p);
 cudaError_t program_run(Program* p, float* acc_ws, cudaStream_t st);
+int program_is_stream(const Program* p);
+size_t program_stream_bytes(const Program* p);
+// stream format (program_stream.cuh; oracle/stream_format.py): one-time re-layout of a GEMM-layout linear
+size_t stream_format_bytes(int K, int N, int G);
+bool stream_format_supported(int K, int N, int G, int mode);
+cudaError_t stream_pack(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out, int K, int N, int G,
+                        int mode, cudaStream_t st);
 void program_destroy(Program* p);
 cudaError_t program_debug_read(void* dst, size_t bytes);
 cudaError_t program_abort_read(void* dst, size_t bytes);

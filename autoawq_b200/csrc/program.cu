@@ -29,6 +29,7 @@
 // mlp) with awq/modules/fused/mlp.py:41-55 (gate/up GEMM, silu*mul, down GEMM), each a separate awq_ext call.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -58,6 +59,7 @@ struct __align__(128) ProgOp {
   int ext_dep;            // >= 0: the external source was written by that (older) op of this program
   int n_part;             // CTAs that share this op's tiles (the first n_part; 0 = all): small ops use fewer, so that
                           // fewer CTAs add into each column block (knob 13 = minimum tiles per participating CTA)
+  const int32_t* qw_src;  // the checkpoint-format qweight (host-side use: the stream variant re-lays it out)
 };
 static_assert(sizeof(ProgOp) == 256, "ProgOp layout");
 
@@ -219,6 +221,10 @@ __device__ __forceinline__ void prog_wait_row_clean(volatile int* red_ok, const 
     if (wd.tick(kWRedOk, op)) break;
   }
 }
+
+}  // namespace b200awq
+#include "program_stream.cuh"
+namespace b200awq {
 
 constexpr int kProgThreads = kV3Threads + 32;   // producer warp + 8 consumer warps + duty warp
 
@@ -686,7 +692,165 @@ struct Program {
   int acc_stride = 0;   // floats per accumulator row (3 rows rotate through the ops)
   size_t xs_bytes = 0;
   int device = 0;
+  // stream variant (program_stream.cuh): re-laid-out weights, per-op CTA partition, hand-off rows, tag state
+  bool stream = false;
+  SpOp* d_sp_ops = nullptr;
+  uint8_t* d_stream = nullptr;
+  uint32_t* d_cta = nullptr;
+  uint32_t* d_rows = nullptr;
+  int* d_state = nullptr;
+  int row_stride = 0;
+  size_t stream_bytes = 0;
 };
+
+size_t stream_format_bytes(int K, int N, int G) {
+  if (K <= 0 || N <= 0 || G <= 0) return 0;
+  const int UK = G < 128 ? G : 128;
+  return (size_t)(N / 16) * (K / UK) * ((size_t)(UK / 16) * 128 + kSpAux);
+}
+bool stream_format_supported(int K, int N, int G, int mode) {
+  if (K <= 0 || N <= 0 || G <= 0 || (K % G) != 0 || (N % 16) != 0 || (K % 128) != 0) return false;
+  if (!(G == 32 || G == 64 || (G % 128) == 0)) return false;
+  if (mode == 1 && ((N / 2) % 8) != 0) return false;
+  return mode == 0 || mode == 1;
+}
+cudaError_t stream_pack(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out, int K, int N, int G,
+                        int mode, cudaStream_t st) {
+  if (!stream_format_supported(K, N, G, mode)) return cudaErrorNotSupported;
+  const int UK = G < 128 ? G : 128;
+  const int64_t total = (int64_t)(N / 16) * (K / UK) * ((UK / 16) * 32 + 12);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  stream_pack_kernel<<<blocks, 256, 0, st>>>(qweight, static_cast<const __half*>(scales), qzeros,
+                                             static_cast<uint8_t*>(out), K, N, G, mode);
+  return cudaGetLastError();
+}
+
+// Builds the stream variant from the folded op table.  Returns false when the sequence is outside its envelope
+// (the caller then tries the split-K kernel).  *err != cudaSuccess reports a CUDA failure.
+static bool stream_build(Program* pr, const std::vector<ProgOp>& table, int grid, cudaError_t* err) {
+  *err = cudaSuccess;
+  const int n = static_cast<int>(table.size());
+  if (n >= 60000) return false;
+  // creation is a load-time step (not capturable): whatever produced the checkpoint tensors on any stream is done
+  // before the re-layout reads them
+  if ((*err = cudaDeviceSynchronize()) != cudaSuccess) return false;
+  std::vector<SpOp> ops(n);
+  std::vector<int> mode(n, 0);
+  // producer-side SiLU*mul: a SILU prologue whose source is the whole output of the previous linear
+  for (int i = 0; i < n; ++i)
+    if (table[i].prologue == kProSilu) {
+      if (i == 0 || !table[i].src_prev || table[i].src_off != 0 || table[i - 1].N != 2 * table[i].K) {
+        // a later consumer of an already fused gate|up output (ext_dep) is fine, anything else is not
+        const int j = table[i].ext_dep;
+        if (!(j >= 0 && mode[j] == 1 && table[i].src == table[j].y && table[j].N == 2 * table[i].K)) return false;
+      } else {
+        mode[i - 1] = 1;
+      }
+    }
+  size_t wbytes = 0, max_cols = 0;
+  int max_K = 0;
+  std::vector<size_t> woff(n);
+  for (int i = 0; i < n; ++i) {
+    const ProgOp& p = table[i];
+    if (!stream_format_supported(p.K, p.N, p.G, mode[i])) return false;
+    const int UK = p.G < 128 ? p.G : 128;
+    if (p.K / UK > kSpXsumMax) return false;
+    if ((p.N / 16 + grid - 1) / grid > kSpLMax) return false;
+    woff[i] = wbytes;
+    wbytes += (stream_format_bytes(p.K, p.N, p.G) + 255) & ~(size_t)255;
+    max_cols = std::max(max_cols, (size_t)(mode[i] ? p.N / 2 : p.N));
+    max_K = std::max(max_K, p.K);
+  }
+  if (sp_fixed_smem() + (size_t)max_K * 2 > (size_t)227 * 1024) return false;
+  for (int i = 0; i < n; ++i) {
+    const ProgOp& p = table[i];
+    SpOp& o = ops[i];
+    std::memset(&o, 0, sizeof(o));
+    o.bias = p.bias;
+    o.y = p.y;
+    o.K = p.K;
+    o.N = p.N;
+    const int UK = p.G < 128 ? p.G : 128;
+    o.uk_shift = UK == 32 ? 5 : (UK == 64 ? 6 : 7);
+    o.F = UK / 16;
+    o.NU = p.K / UK;
+    o.unit_bytes = o.F * 128 + kSpAux;
+    o.ups = kSpStageBytes / o.unit_bytes;
+    o.mode = mode[i];
+    o.eps = p.eps;
+    o.norm_w = p.norm_w;
+    o.src_op = -1;
+    if (p.prologue == kProSilu) {
+      // the SiLU*mul itself runs in the producer (mode 1); this op copies the published product
+      const int j = p.src_prev ? i - 1 : p.ext_dep;
+      if (i - j >= kSpRows) return false;
+      o.prologue = kProCopy;
+      o.src_op = j;
+      o.src_off = 0;
+      if (p.xout != nullptr) ops[j].act_out = p.xout;
+    } else {
+      o.prologue = p.prologue;
+      o.xout = p.prologue == kProRmsnorm ? p.xout : nullptr;
+      if (p.prologue == kProCopy && p.xout != nullptr) return false;
+      int j = -1;
+      if (p.src_prev) j = i - 1;
+      else if (p.ext_dep >= 0) j = p.ext_dep;
+      if (j >= 0) {
+        if (mode[j] == 1 || i - j >= kSpRows) return false;   // raw gate|up columns of a fused producer / row recycled
+        const uintptr_t y0 = reinterpret_cast<uintptr_t>(table[j].y), s0 = reinterpret_cast<uintptr_t>(p.src);
+        if (s0 < y0 || s0 + (size_t)p.K * 2 > y0 + (size_t)table[j].N * 2 || ((s0 - y0) & 7) != 0) return false;
+        o.src_op = j;
+        o.src_off = static_cast<int>((s0 - y0) / 2);
+      } else {
+        o.src = p.src;
+        if ((reinterpret_cast<uintptr_t>(p.src) & 7) != 0) return false;
+      }
+    }
+  }
+  // CTA partition: whole 16-column sets, as even as the set count allows
+  std::vector<uint32_t> cta((size_t)n * (grid + 1));
+  for (int i = 0; i < n; ++i) {
+    const int64_t S = table[i].N / 16;
+    for (int c = 0; c <= grid; ++c) cta[(size_t)i * (grid + 1) + c] = (uint32_t)((S * c / grid) * ops[i].NU);
+  }
+  pr->row_stride = (int)((max_cols + 63) & ~(size_t)63);
+  cudaError_t e = cudaMalloc(&pr->d_stream, wbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&pr->d_sp_ops, (size_t)n * sizeof(SpOp));
+  if (e == cudaSuccess) e = cudaMalloc(&pr->d_cta, cta.size() * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&pr->d_rows, (size_t)kSpRows * pr->row_stride * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&pr->d_state, 2 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(pr->d_rows, 0, (size_t)kSpRows * pr->row_stride * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(pr->d_state, 0, 2 * sizeof(int));
+  for (int i = 0; i < n && e == cudaSuccess; ++i) {
+    ops[i].wstream = pr->d_stream + woff[i];
+    ops[i].cta_begin = pr->d_cta + (size_t)i * (grid + 1);
+    e = stream_pack(table[i].qw_src, table[i].scales, table[i].qzeros, pr->d_stream + woff[i], table[i].K, table[i].N,
+                    table[i].G, mode[i], nullptr);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(pr->d_sp_ops, ops.data(), (size_t)n * sizeof(SpOp), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(pr->d_cta, cta.data(), cta.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(stream_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(pr->d_stream);
+    cudaFree(pr->d_sp_ops);
+    cudaFree(pr->d_cta);
+    cudaFree(pr->d_rows);
+    cudaFree(pr->d_state);
+    pr->d_stream = nullptr;
+    pr->d_sp_ops = nullptr;
+    pr->d_cta = nullptr;
+    pr->d_rows = nullptr;
+    pr->d_state = nullptr;
+    *err = e;
+    return false;
+  }
+  pr->stream = true;
+  pr->stream_bytes = wbytes;
+  pr->xs_bytes = (size_t)max_K * 2;
+  return true;
+}
 
 static int prog_sm_count() {
   int dev = 0, n = 0;
@@ -731,6 +895,7 @@ int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* c
   std::vector<Glue> glues;
   const int grid = prog_sm_count();
   int max_K = 0, max_N = 0, M = -1;
+  bool v3_ok = true;
   for (int i = 0; i < n; ++i) {
     const b200awq_op_t& op = ops[i];
     if (M < 0) M = op.M;
@@ -761,17 +926,22 @@ int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* c
       return B200AWQ_EINVAL;
     GemmArgs a{op.x, op.ldx, static_cast<const int32_t*>(op.qweight), op.scales, static_cast<const int32_t*>(op.qzeros),
                op.bias, op.y, op.M, op.K, op.N, op.group_size};
-    if (M != 1 || !gemv_v3_supported(a)) return B200AWQ_EUNSUPPORTED;
-    if ((op.N / kV3TileCols) * (op.K / kV3TileRows) < grid) return B200AWQ_EUNSUPPORTED;  // every CTA owns tiles
-    if (op.K / kV3TileRows >= 256) return B200AWQ_EUNSUPPORTED;   // tile count per column must fit the packed word
+    if (M != 1) return B200AWQ_EUNSUPPORTED;
+    // envelope of the split-K kernel (the stream variant has its own, checked in stream_build)
+    if (!gemv_v3_supported(a) || (op.N / kV3TileCols) * (op.K / kV3TileRows) < grid ||   // every CTA owns tiles
+        op.K / kV3TileRows >= 256)                                                       // tiles per column fit the packed word
+      v3_ok = false;
     ProgOp p;
     std::memset(&p, 0, sizeof(p));
     p.ext_dep = -1;
-    cudaError_t e = make_tmap_2d(a.qweight, /*int32*/ 1, (uint64_t)(a.N / 8), (uint64_t)a.K, (uint64_t)(a.N / 8) * 4, 32,
-                                 kV3TileRows, &p.tmw);
-    if (e != cudaSuccess) {
-      *cuda_err = e;
-      return B200AWQ_ECUDA;
+    p.qw_src = a.qweight;
+    if (v3_ok) {
+      cudaError_t e = make_tmap_2d(a.qweight, /*int32*/ 1, (uint64_t)(a.N / 8), (uint64_t)a.K, (uint64_t)(a.N / 8) * 4, 32,
+                                   kV3TileRows, &p.tmw);
+      if (e != cudaSuccess) {
+        *cuda_err = e;
+        return B200AWQ_ECUDA;
+      }
     }
     p.scales = static_cast<const __half*>(op.scales);
     p.qzeros = static_cast<const int32_t*>(op.qzeros);
@@ -847,16 +1017,29 @@ int program_create(const b200awq_op_t* ops, int n, Program** out, cudaError_t* c
   for (const Glue& gl : glues)
     if (!gl.used) return B200AWQ_EUNSUPPORTED;   // a glue op nobody consumes would never run
   if (table.empty()) return B200AWQ_EUNSUPPORTED;
-  const size_t smem = prog_fixed_smem(2) + (size_t)(max_K + 8) * 2 * kProgMT;
-  if (smem > (size_t)227 * 1024) return B200AWQ_EUNSUPPORTED;
 
   Program* pr = new Program();
   pr->n_ops = static_cast<int>(table.size());
   pr->M = M;
   pr->max_N = max_N;
+  cudaError_t e = cudaGetDevice(&pr->device);
+  // first choice: the stream variant (one-time re-layout, output-stationary partition); knob 14 = 1 skips it
+  if (e == cudaSuccess && knob(14) != 1 && stream_build(pr, table, grid, &e)) {
+    *out = pr;
+    return B200AWQ_OK;
+  }
+  if (e != cudaSuccess) {
+    delete pr;
+    *cuda_err = e;
+    return B200AWQ_ECUDA;
+  }
+  const size_t smem = prog_fixed_smem(2) + (size_t)(max_K + 8) * 2 * kProgMT;
+  if (!v3_ok || knob(14) == 2 || smem > (size_t)227 * 1024) {
+    delete pr;
+    return B200AWQ_EUNSUPPORTED;
+  }
   pr->acc_stride = (max_N + 7) & ~7;
   pr->xs_bytes = (size_t)(max_K + 8) * 2 * kProgMT;
-  cudaError_t e = cudaGetDevice(&pr->device);
   if (e == cudaSuccess) e = cudaMalloc(&pr->d_ops, table.size() * sizeof(ProgOp));
   if (e == cudaSuccess) e = cudaMalloc(&pr->d_done, 2 * (table.size() + 1) * sizeof(int));
   if (e == cudaSuccess) e = cudaMemcpy(pr->d_ops, table.data(), table.size() * sizeof(ProgOp), cudaMemcpyHostToDevice);
@@ -879,10 +1062,27 @@ int program_max_n(const Program* p) { return p->max_N; }
 int program_m(const Program* p) { return p->M; }
 int program_num_ops(const Program* p) { return p->n_ops; }
 
+int program_is_stream(const Program* p) { return p->stream ? 1 : 0; }
+size_t program_stream_bytes(const Program* p) { return p->stream_bytes; }
+
 cudaError_t program_run(Program* p, float* acc_ws, cudaStream_t st) {
   // staged[] and zeroed[] counters (see program_kernel)
   cudaError_t e = program_abort_clear(st);
   if (e != cudaSuccess) return e;
+  if (p->stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(prog_sm_count());
+    cfg.blockDim = dim3(kSpThreads);
+    cfg.dynamicSmemBytes = sp_fixed_smem() + p->xs_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the hand-off polls are grid-wide waits
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const SpOp* sops = p->d_sp_ops;
+    return cudaLaunchKernelEx(&cfg, stream_program_kernel, sops, p->n_ops, p->d_rows, p->row_stride, p->d_state, knob(3));
+  }
   e = cudaMemsetAsync(p->d_done, 0, (size_t)2 * (p->n_ops + 1) * sizeof(int), st);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
@@ -913,6 +1113,11 @@ void program_destroy(Program* p) {
   if (p == nullptr) return;
   cudaFree(p->d_ops);
   cudaFree(p->d_done);
+  cudaFree(p->d_sp_ops);
+  cudaFree(p->d_stream);
+  cudaFree(p->d_cta);
+  cudaFree(p->d_rows);
+  cudaFree(p->d_state);
   delete p;
 }
 

@@ -17,7 +17,7 @@ __all__ = [
     "gemm_forward_cuda", "dequantize_weights_cuda", "gemv_forward_cuda", "gemmv2_forward_cuda",
     "gemv_forward_cuda_decode", "gemm_forward_cuda_prefill", "layernorm_forward_cuda", "silu_and_mul",
     "topk_softmax", "moe_alig_block_size", "grouped_gemm_forward",
-    "linear_forward", "set_knob", "get_knob", "B200AwqError",
+    "linear_forward", "stream_pack", "set_knob", "get_knob", "B200AwqError",
 ]
 
 _WS: dict = {}
@@ -283,6 +283,26 @@ def gemm_forward_cuda_prefill(x, qweight, scales, szeros):
     K = qweight.shape[1]
     out = linear_forward("fast", x, qweight, scales, szeros, _fast_group_size(K, scales.shape[0]))
     return out.reshape(x.shape[:-1] + (out.shape[-1],))
+
+
+def stream_pack(qweight, scales, qzeros, mode: int = 0) -> torch.Tensor:
+    """One-time re-layout of a GEMM-layout linear into the stream format the decode-program kernel reads
+    (include/b200awq.h; the post_init-style hook, cf. awq/modules/linear/exllama.py:66-79).  Returns a uint8 tensor."""
+    _require_cuda(qweight, scales, qzeros)
+    _check_w(qweight, torch.int32, "qweight")
+    _check_w(scales, torch.float16, "scales")
+    _check_w(qzeros, torch.int32, "qzeros")
+    K, N = qweight.shape[0], qweight.shape[1] * 8
+    G = K // scales.shape[0]
+    nbytes = lib.b200awq_stream_bytes(K, N, G)
+    if nbytes == 0:
+        raise B200AwqError(f"b200awq: no stream format for K={K}, N={N}, G={G}")
+    out = torch.empty(nbytes, dtype=torch.uint8, device=qweight.device)
+    with _DeviceGuard(qweight.device):
+        code = lib.b200awq_stream_pack(qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(), out.data_ptr(), K, N, G,
+                                       int(mode), _stream(qweight.device))
+    check(code, f"b200awq_stream_pack(K={K}, N={N}, G={G}, mode={mode})")
+    return out
 
 
 def set_knob(key: int, value: int) -> None:

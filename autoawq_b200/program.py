@@ -128,6 +128,14 @@ class DecodeProgram:
         return self._handle is not None
 
     @property
+    def kind(self) -> str:
+        """"stream" (re-laid-out weights, output-stationary kernel), "splitk" (round-1 kernel on the checkpoint
+        layout) or "per-op"."""
+        if self._handle is None:
+            return "per-op"
+        return "stream" if lib.b200awq_program_kind(self._handle) == 2 else "splitk"
+
+    @property
     def kernel_ops(self) -> int:
         return lib.b200awq_program_num_ops(self._handle) if self._handle is not None else 0
 

@@ -479,6 +479,8 @@ def main():
         prog.build()
         if not prog.fused:
             prog = None
+        else:
+            config["program_kind"] = prog.kind
 
     # per-op path: the step replayed as one CUDA graph of 224 kernel launches
     g_ops, out_ops = capture(torch, lambda: rep.step(rep.h))
@@ -524,7 +526,8 @@ def main():
                 # dram__bytes_read + write per program_kernel launch: profiles/r01_ncu_program_kernel_bench.csv
                 # (3,629.7 MB read + 27-29 MB written; algorithmic 3,626 MB)
                 "traffic": 3658000000 if a.layers == LAYERS else None,
-                "kernel": "program_kernel (persistent decode program: 128 linears + glue per launch)",
+                "kernel": ("stream_program_kernel" if prog.kind == "stream" else "program_kernel") +
+                          " (persistent decode program: 128 linears + glue per launch)",
                 "peak_src": peaks["src"] + " (hbm_gbs)",
                 "per_launch": {"avg_us": round(step_s * 1e6, 2), "alg_bytes": alg_bytes,
                                "launches_timed": a.steps,

@@ -143,6 +143,8 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *   key 12: 2 = grouped_gemm_forward always uses the register-staged grouped kernel
  *   key 13: decode program (read at b200awq_program_create): minimum tiles per participating CTA; ops with fewer
  *           tiles per CTA are shared by fewer CTAs (0 = every CTA takes part in every op, the default: measured best)
+ *   key 14: decode program kind (read at b200awq_program_create): 0 = stream variant when the sequence fits it,
+ *           else the split-K kernel; 1 = split-K kernel only; 2 = stream variant only
  */
 int b200awq_set_knob(int key, int value);
 int b200awq_get_knob(int key);
@@ -187,12 +189,31 @@ typedef struct b200awq_op {
 typedef struct b200awq_program* b200awq_program_t;
 
 int b200awq_program_create(const b200awq_op_t* ops, int n_ops, b200awq_program_t* out);
+/* 0: null handle; 1: split-K kernel on the checkpoint layout (round 1); 2: stream variant - at creation every
+ * linear of the program was re-laid-out once into the stream format (below), the kernel partitions the work
+ * output-stationary and hands activations from op to op as tagged fp16 words (csrc/program_stream.cuh).  Creation
+ * prefers 2 and falls back to 1 (shapes / aliasing outside its envelope; knob 14 = 1 forces 1, 2 forbids 1). */
+int b200awq_program_kind(b200awq_program_t prog);
 /* number of fused kernel ops (= linear ops) of the program; 0 for a null handle */
 int b200awq_program_num_ops(b200awq_program_t prog);
 /* workspace: b200awq_workspace_bytes(8, K, max N over the program's linears rounded up to 8): four rows of 64-bit
  * packed split-K sums; zero-initialised and left all-zero like the per-op workspace (the same buffer may serve both) */
 int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
 int b200awq_program_destroy(b200awq_program_t prog);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Stream format: the one-time, load-time re-layout of a GEMM-layout linear that the decode-program kernel
+ * streams (the reference's precedent for a post-load re-layout is WQLinear_Exllama.post_init,
+ * awq/modules/linear/exllama.py:66-79; the checkpoint format and the module API stay the reference's).  Layout:
+ * oracle/stream_format.py (numpy restatement, bit-compared with this entry point in the tests).  Columns are taken
+ * in sets of 16, K in units of min(G, 128) rows; a unit is contiguous (fragments in mma.m16n8k16 A-operand order +
+ * the unit's scales / zeros), the buffer is set-major, so any partition of the work is a contiguous byte range.
+ * mode 0: set s = columns 16 s .. 16 s + 15; mode 1 (a fused gate|up linear): gate column j and up column j share
+ * a lane, so SiLU*mul happens in the producer.  Requires N % 16 == 0, K % 128 == 0, G in {32, 64} or G % 128 == 0.
+ * b200awq_stream_bytes returns 0 for unsupported shapes. */
+size_t b200awq_stream_bytes(int K, int N, int group_size);
+int b200awq_stream_pack(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out, int K, int N,
+                        int group_size, int mode, b200awq_stream_t stream);
 
 #ifdef __cplusplus
 }

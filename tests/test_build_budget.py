@@ -22,7 +22,10 @@ def test_program_kernel_register_and_spill_budget(tmp_path):
     log = out.stderr + out.stdout
     entries = re.findall(r"Compiling entry function '(\S*program_kernel\S*)'[^\n]*\n[^\n]*\n\s*(\d+) bytes stack frame, "
                          r"(\d+) bytes spill stores, (\d+) bytes spill loads\n[^\n]*Used (\d+) registers", log)
-    assert len(entries) == 2, log[-1500:]          # program_kernel<1>, program_kernel<2>
+    assert len(entries) == 3, log[-1500:]          # program_kernel<1>, program_kernel<2>, stream_program_kernel
+    assert sum("stream_program_kernel" in e[0] for e in entries) == 1
     for name, stack, st, ld, regs in entries:
         assert int(st) == 0 and int(ld) == 0 and int(stack) == 0, f"{name}: spills"
-        assert int(regs) <= 204, f"{name}: {regs} registers x 320 threads exceed the register file"
+        # split-K kernel: 320 threads -> 204 registers; stream kernel: 288 threads -> 227
+        lim = 227 if "stream_program_kernel" in name else 204
+        assert int(regs) <= lim, f"{name}: {regs} registers exceed the register file for one resident CTA"

@@ -107,18 +107,27 @@ def small_blocks():
     return [Block(2048, 4096, 3072, 128, seed=s) for s in (1, 2)]
 
 
+@pytest.fixture(params=["stream", "splitk"])
+def kind(request, api):
+    """Both program kernels: the stream variant (one-time re-layout, csrc/program_stream.cuh; the default) and the
+    split-K kernel on the checkpoint layout (csrc/program.cu; knob 14 = 1)."""
+    api.set_knob(14, 2 if request.param == "stream" else 1)
+    yield request.param
+    api.set_knob(14, 0)
+
+
 def _h0(hidden, M, seed=0):
     return _t(np.random.default_rng(seed).standard_normal((M, hidden)).astype(np.float16))
 
 
-def test_program_matches_oracle_op_by_op(api, small_blocks):
+def test_program_matches_oracle_op_by_op(api, small_blocks, kind):
     from autoawq_b200.program import DecodeProgram
 
     h = _h0(2048, 1)
     prog = DecodeProgram()
     bufs = _record(prog, small_blocks, h, 1)
     prog.build()
-    assert prog.fused and prog.kernel_ops == 8 and prog.launches_per_run == 1
+    assert prog.fused and prog.kernel_ops == 8 and prog.launches_per_run == 1 and prog.kind == kind
     prog.run()
     torch.cuda.synchronize()
     _check_against_oracle(small_blocks, bufs, "program")
@@ -134,7 +143,7 @@ def test_program_matches_oracle_op_by_op(api, small_blocks):
     assert torch.equal(bufs[0]["xn"], ref[0]["xn"])
 
 
-def test_program_replays_and_leaves_scratch_clean(api, small_blocks):
+def test_program_replays_and_leaves_scratch_clean(api, small_blocks, kind):
     from autoawq_b200.program import DecodeProgram
 
     h = _h0(2048, 1, seed=3)
@@ -161,7 +170,7 @@ def test_program_replays_and_leaves_scratch_clean(api, small_blocks):
         assert int(ws.count_nonzero()) == 0, "program left the shared workspace dirty"
 
 
-def test_program_is_bit_reproducible(api):
+def test_program_is_bit_reproducible(api, kind):
     """The split-K sums travel as integers (csrc/program.cu, packed hand-off): the result does not depend on the order
     in which CTAs arrive, so two runs on the same input must agree bit for bit - at the Llama-3-8B shapes, where
     every column block has ~10 contributors."""
@@ -184,7 +193,7 @@ def test_program_is_bit_reproducible(api):
     _no_abort("reproducibility")
 
 
-def test_program_in_cuda_graph(api, small_blocks):
+def test_program_in_cuda_graph(api, small_blocks, kind):
     from autoawq_b200.program import DecodeProgram
 
     h = _h0(2048, 1, seed=5)
@@ -239,7 +248,7 @@ def test_program_rejects_unconsumed_glue_and_aliasing(api, small_blocks):
     torch.cuda.synchronize()
 
 
-def test_program_llama8b_layer_shapes(api):
+def test_program_llama8b_layer_shapes(api, kind):
     """BASELINE config 2 shapes (Llama-3-8B, g128): two full-size blocks, program vs oracle op by op."""
     from autoawq_b200.program import DecodeProgram
 
@@ -248,14 +257,14 @@ def test_program_llama8b_layer_shapes(api):
     prog = DecodeProgram()
     bufs = _record(prog, blocks, h, 1)
     prog.build()
-    assert prog.fused and prog.kernel_ops == 8
+    assert prog.fused and prog.kernel_ops == 8 and prog.kind == kind
     for _ in range(3):
         prog.run()
     torch.cuda.synchronize()
     _check_against_oracle(blocks, bufs, "program 8B shapes")
 
 
-def test_program_bias_group64_and_older_source(api):
+def test_program_bias_group64_and_older_source(api, kind):
     """Paths the Llama chain does not touch: linears with a bias (added before the fp16 rounding, as the per-op path
     does), group size 64, and a linear whose source is the output of an op OLDER than its predecessor (read back from
     global memory after that op's duty-warp stores, `ext_dep`)."""
@@ -273,7 +282,7 @@ def test_program_bias_group64_and_older_source(api):
     y1 = prog.gemm_forward_cuda(y0, _t(cs[1]["qweight"]), _t(sc[1]), _t(cs[1]["qzeros"]), 8, bias=_t(bias[1]))
     y2 = prog.gemm_forward_cuda(y0, _t(cs[2]["qweight"]), _t(sc[2]), _t(cs[2]["qzeros"]), 8, bias=_t(bias[2]))  # older src
     prog.build()
-    assert prog.fused and prog.kernel_ops == 3
+    assert prog.fused and prog.kernel_ops == 3 and prog.kind == kind
     for _ in range(3):
         prog.run()
     torch.cuda.synchronize()
@@ -283,3 +292,52 @@ def test_program_bias_group64_and_older_source(api):
         ref = O.gemm_f64(xin[i], ws[i]) + bias[i].astype(np.float64)
         budget = np.abs(xin[i].astype(np.float64)) @ np.abs(ws[i].astype(np.float64))
         _close(y.cpu().numpy(), ref, budget, f"op {i}")
+
+
+# ------------------------------------------------------------------------------------- the stream format itself
+@pytest.mark.parametrize("K,N,G,mode", [(256, 32, 128, 0), (128, 32, 32, 0), (256, 48, 64, 0), (256, 64, 128, 1),
+                                        (512, 32, -1, 0), (4096, 4096, 128, 0), (4096, 28672, 128, 1)])
+def test_stream_pack_bit_exact_vs_oracle(api, K, N, G, mode):
+    """b200awq_stream_pack (the one-time re-layout) against its numpy restatement
+    (oracle/stream_format.py, itself pinned to the reference's dequantize_gemm semantics in the CPU tests)."""
+    from oracle import stream_format as SF
+
+    c = O.make_case(K, N, G, seed=K + N + mode, raw=True)
+    Gs = c["group_size"]
+    got = api.stream_pack(_t(c["qweight"]), _t(c["scales"]), _t(c["qzeros"]), mode).cpu().numpy()
+    want = SF.pack_stream(c["qweight"], c["qzeros"], c["scales"], Gs, mode)
+    assert got.size == SF.stream_bytes(K, N, Gs) == want.size
+    assert np.array_equal(got, want)
+
+
+def test_stream_program_general_groups_and_small_shapes(api):
+    """Stream variant outside the Llama shapes: G = 32 / 64 / per-channel (G = K), N not a multiple of 256, a chain of
+    plain copies; every op against the oracle."""
+    from autoawq_b200.program import DecodeProgram
+
+    api.set_knob(14, 2)
+    try:
+        rng = np.random.default_rng(3)
+        dims = [(512, 1024, 32), (1024, 1936, 64), (1920, 512, 128)]   # op 2 reads columns 16 .. 1935 of op 1's output
+        cs, scs, ws = [], [], []
+        for K, N, G in dims:
+            c = O.make_case(K, N, G, seed=K)
+            sc = (c["scales"].astype(np.float32) / (6.1 * 0.0108 * np.sqrt(K))).astype(np.float16)
+            cs.append(c); scs.append(sc); ws.append(O.dequantize_gemm(c["qweight"], c["qzeros"], sc, c["group_size"]))
+        x = _t(rng.standard_normal((1, 512)).astype(np.float16))
+        prog = DecodeProgram()
+        y0 = prog.gemm_forward_cuda(x, _t(cs[0]["qweight"]), _t(scs[0]), _t(cs[0]["qzeros"]), 8)
+        y1 = prog.gemm_forward_cuda(y0, _t(cs[1]["qweight"]), _t(scs[1]), _t(cs[1]["qzeros"]), 8)
+        y2 = prog.gemm_forward_cuda(y1[:, 16:1936], _t(cs[2]["qweight"]), _t(scs[2]), _t(cs[2]["qzeros"]), 8)
+        prog.build()
+        assert prog.kind == "stream"
+        for _ in range(2):
+            prog.run()
+        torch.cuda.synchronize()
+        _no_abort("stream general")
+        xin = [x.cpu().numpy(), y0.cpu().numpy(), y1.cpu().numpy()[:, 16:1936]]
+        for i, y in enumerate((y0, y1, y2)):
+            budget = np.abs(xin[i].astype(np.float64)) @ np.abs(ws[i].astype(np.float64))
+            _close(y.cpu().numpy(), O.gemm_f64(xin[i], ws[i]), budget, f"stream general op {i}")
+    finally:
+        api.set_knob(14, 0)
