@@ -191,6 +191,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the calling thread for a system-dependent time; a warp whose lanes poll
+// DIFFERENT barriers must not let one lane's suspension stall the others: see the converged producer loops)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -216,6 +229,10 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int
 // L2 prefetch hint for one 128-byte line (a hint: dropped, not faulted, if the address cannot be translated)
 __device__ __forceinline__ void prefetch_l2_line(const void* gsrc) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(gsrc) : "memory");
+}
+// L2 prefetch of a contiguous range (size % 16 == 0), no completion tracking
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 // 1-D bulk copy global -> smem (no tensor map), completion on mbarrier (bytes); size % 16 == 0
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

@@ -93,6 +93,7 @@ cudaError_t stream_pack(const int32_t* qweight, const void* scales, const int32_
 void program_destroy(Program* p);
 cudaError_t program_debug_read(void* dst, size_t bytes);
 cudaError_t program_abort_read(void* dst, size_t bytes);
+cudaError_t stream_debug_read(void* dst, size_t bytes);
 
 // grouped persistent GEMV (gemv.cu): the decode-size path of grouped_gemm_forward
 bool gemv_v3_moe_supported(int K, int N, int G, int hbs);

@@ -761,7 +761,7 @@ static bool stream_build(Program* pr, const std::vector<ProgOp>& table, int grid
     max_cols = std::max(max_cols, (size_t)(mode[i] ? p.N / 2 : p.N));
     max_K = std::max(max_K, p.K);
   }
-  if (sp_fixed_smem() + (size_t)max_K * 2 > (size_t)227 * 1024) return false;
+  if (sp_fixed_smem(12, 3) + (size_t)max_K * 2 > (size_t)227 * 1024) return false;   // (the largest configuration)
   for (int i = 0; i < n; ++i) {
     const ProgOp& p = table[i];
     SpOp& o = ops[i];
@@ -830,7 +830,11 @@ static bool stream_build(Program* pr, const std::vector<ProgOp>& table, int grid
   if (e == cudaSuccess) e = cudaMemcpy(pr->d_sp_ops, ops.data(), (size_t)n * sizeof(SpOp), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(pr->d_cta, cta.data(), cta.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(stream_program_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    e = cudaFuncSetAttribute(stream_program_kernel<8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(stream_program_kernel<12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(stream_program_kernel<16, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     cudaFree(pr->d_stream);
@@ -1070,10 +1074,14 @@ cudaError_t program_run(Program* p, float* acc_ws, cudaStream_t st) {
   cudaError_t e = program_abort_clear(st);
   if (e != cudaSuccess) return e;
   if (p->stream) {
+    // knob 9: consumer warps of the stream kernel: 8 (4 ring stages each, 4 units in flight; the default: measured
+    // best, 1.50 / 1.59 / 1.73 ms per Llama-3-8B step with 8 / 12 / 16), 12 (3 stages, 2 units) or 16 (2 stages, 2 units)
+    const int nw = knob(9) == 12 ? 12 : (knob(9) == 16 ? 16 : 8);
+    const int spw = nw == 8 ? 4 : (nw == 12 ? 3 : 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(prog_sm_count());
-    cfg.blockDim = dim3(kSpThreads);
-    cfg.dynamicSmemBytes = sp_fixed_smem() + p->xs_bytes;
+    cfg.blockDim = dim3(32 + nw * 32);
+    cfg.dynamicSmemBytes = sp_fixed_smem(nw, spw) + p->xs_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: the hand-off polls are grid-wide waits
@@ -1081,7 +1089,21 @@ cudaError_t program_run(Program* p, float* acc_ws, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const SpOp* sops = p->d_sp_ops;
-    return cudaLaunchKernelEx(&cfg, stream_program_kernel, sops, p->n_ops, p->d_rows, p->row_stride, p->d_state, knob(3));
+    const uint32_t* cta = p->d_cta;
+    // knob 8: HBM -> L2 prefetch window per producer lane in KB (<= 0 = off, the default: it helps only when the weight
+    // stream is the bottleneck - 1041 -> 895 us without the unit math - and costs 1-6 % with it)
+    const int l2_ahead = knob(8) <= 0 ? 0 : knob(8) * 1024;
+    // knob 10: ops ahead of the consumers' staging for which shared-memory loads may already be issued (0 = ungated,
+    // the default; n > 0: at most n - 1 ops ahead, 1 = strictly gated)
+    const int gate_ahead = knob(10) <= 0 ? 1 << 20 : knob(10) - 1;
+    if (nw == 8)
+      return cudaLaunchKernelEx(&cfg, stream_program_kernel<8, 4, 4>, sops, cta, p->n_ops, p->d_rows, p->row_stride,
+                                p->d_state, knob(3), l2_ahead, gate_ahead);
+    if (nw == 16)
+      return cudaLaunchKernelEx(&cfg, stream_program_kernel<16, 2, 2>, sops, cta, p->n_ops, p->d_rows, p->row_stride,
+                                p->d_state, knob(3), l2_ahead, gate_ahead);
+    return cudaLaunchKernelEx(&cfg, stream_program_kernel<12, 3, 2>, sops, cta, p->n_ops, p->d_rows, p->row_stride,
+                              p->d_state, knob(3), l2_ahead, gate_ahead);
   }
   e = cudaMemsetAsync(p->d_done, 0, (size_t)2 * (p->n_ops + 1) * sizeof(int), st);
   if (e != cudaSuccess) return e;

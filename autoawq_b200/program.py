@@ -34,6 +34,7 @@ class DecodeProgram:
         self._built = False
         self._max_n = 0
         self._dev = None
+        self.calibration = None       # {"stream_ms", "splitk_ms"} when build() timed both kernels
 
     # ------------------------------------------------------------------ recording (awq_ext call names)
     def _dev_of(self, t: torch.Tensor):
@@ -107,19 +108,64 @@ class DecodeProgram:
                 c.y = o["y"].data_ptr()
         return arr
 
-    def build(self) -> "DecodeProgram":
+    def _create(self, arr, kind_knob: int):
+        """b200awq_program_create under knob 14 = kind_knob; returns a handle or None (sequence outside that kernel)."""
+        prev = lib.b200awq_get_knob(14)
+        lib.b200awq_set_knob(14, kind_knob)
+        try:
+            handle = ctypes.c_void_p()
+            with ext._DeviceGuard(self._dev):
+                code = lib.b200awq_program_create(arr, len(self._ops), ctypes.byref(handle))
+        finally:
+            lib.b200awq_set_knob(14, prev)
+        if code == _cabi.EUNSUPPORTED:
+            return None
+        check(code, "b200awq_program_create")
+        return handle
+
+    def _time(self, handle, runs: int = 5) -> float:
+        """Median device time (ms) of one run of `handle` on the current stream (load-time calibration)."""
+        dev = self._dev
+        with ext._DeviceGuard(dev):
+            st = ext._stream(dev)
+            ws = ext._workspace(dev, st, lib.b200awq_workspace_bytes(8, 0, (self._max_n + 7) & ~7))
+            ts = []
+            for i in range(runs + 2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                check(lib.b200awq_program_run(handle, ws.data_ptr(), ws.numel(), st), "b200awq_program_run")
+                e1.record()
+                e1.synchronize()
+                if i >= 2:
+                    ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    def build(self, calibrate: bool = True) -> "DecodeProgram":
+        """Fold the recorded calls into a fused program.  Two kernels can run it: the stream variant (one-time
+        re-layout of the weights, output-stationary, csrc/program_stream.cuh) and the split-K kernel on the checkpoint
+        layout (csrc/program.cu).  With `calibrate` (default) and knob 14 = 0, both are created when the sequence fits
+        both, each is timed on the device (a load-time step, like the re-layout itself; the recorded buffers are
+        overwritten by those runs exactly as `run()` would), and the faster one is kept - `calibration` holds the two
+        times.  Knob 14 = 1 / 2 forces the split-K / stream kernel."""
         self._no_more()
         if not self._ops:
             raise B200AwqError("b200awq: empty program")
         arr = self._c_ops()
-        handle = ctypes.c_void_p()
-        with ext._DeviceGuard(self._dev):
-            code = lib.b200awq_program_create(arr, len(self._ops), ctypes.byref(handle))
-        if code == _cabi.EUNSUPPORTED:
-            self._handle = None       # per-op replay (still the CUDA path)
+        self.calibration = None
+        forced = lib.b200awq_get_knob(14)
+        if forced in (1, 2) or not calibrate:
+            self._handle = self._create(arr, forced)
         else:
-            check(code, "b200awq_program_create")
-            self._handle = handle
+            hs, hk = self._create(arr, 2), self._create(arr, 1)
+            if hs is not None and hk is not None:
+                ts, tk = self._time(hs), self._time(hk)
+                self.calibration = {"stream_ms": round(ts, 4), "splitk_ms": round(tk, 4)}
+                keep, drop = (hs, hk) if ts <= tk else (hk, hs)
+                lib.b200awq_program_destroy(drop)
+                self._handle = keep
+            else:
+                self._handle = hs if hs is not None else hk      # None: per-op replay (still the CUDA path)
         self._built = True
         return self
 

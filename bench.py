@@ -481,6 +481,7 @@ def main():
             prog = None
         else:
             config["program_kind"] = prog.kind
+            config["program_calibration"] = prog.calibration
 
     # per-op path: the step replayed as one CUDA graph of 224 kernel launches
     g_ops, out_ops = capture(torch, lambda: rep.step(rep.h))

@@ -17,7 +17,9 @@ from autoawq_b200.program import DecodeProgram  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--layers", type=int, default=4)
+ap.add_argument("--kind", type=int, default=0, help="knob 14: 0 = default (stream), 1 = split-K kernel")
 a = ap.parse_args()
+ext.set_knob(14, a.kind)
 dev = torch.device("cuda:0")
 G, H, I = 128, 4096, 14336
 LIN = [("qkv", H, 6144), ("o", H, H), ("gate_up", H, 2 * I), ("down", I, H)]
@@ -64,7 +66,10 @@ for it in range(6):
         runs.append(buf[: min(nops, 32)].astype(np.int64))
 ext.set_knob(3, 0)
 r = np.stack(runs)  # [runs, ops, cta, 8]
-names = ["begin", "prev done", "x staged", "1st tile", "warp0 done", "all warps", "sums added", "published"]
+stream = prog.kind == "stream"
+names = (["begin", "row polled", "x staged", "1st chunk", "warp0 done", "all warps", "published", "-"] if stream else
+         ["begin", "prev done", "x staged", "1st tile", "warp0 done", "all warps", "sums added", "published"])
+print("program kind:", prog.kind)
 print(f"{nops} kernel ops; ns relative to the op's begin on its earliest CTA (median over 8 CTAs, median over runs)")
 print("op  shape        " + " ".join(f"{n:>10s}" for n in names) + "   next-begin")
 for op in range(min(nops, 32)):
@@ -75,5 +80,5 @@ for op in range(min(nops, 32)):
         nb = f"{np.median(np.median(r[:, op + 1, :, 0] - t0[:, :, 0], axis=1)):10.0f}"
     n, K, N = LIN[op % 4]
     print(f"{op:2d}  {n:8s}     " + " ".join(f"{v:10.0f}" for v in d) + "   " + nb)
-tot = r[:, min(nops, 32) - 1, :, 7].max(axis=1) - r[:, 0, :, 0].min(axis=1)
+tot = r[:, min(nops, 32) - 1, :, 6 if stream else 7].max(axis=1) - r[:, 0, :, 0].min(axis=1)
 print("span first begin -> last published (ns):", np.median(tot), " per op:", np.median(tot) / min(nops, 32))
