@@ -4,13 +4,29 @@
 #include <cstdio>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>   // header-only (the tools library is loaded lazily, and only when a profiler is attached)
+
 #include "../../include/b200awq.h"
 #include "kernels.h"
 
 namespace b200awq {
 
+// NVTX range around one operator call when knob 15 is set ("NVTX ranges per WQLinear call"): the ranges
+// show up in Nsight Systems / ncu --nvtx timelines; off (the default) costs one relaxed atomic load.
+struct NvtxScope {
+  bool on;
+  explicit NvtxScope(const char* name);
+  ~NvtxScope() {
+    if (on) nvtxRangePop();
+  }
+};
+
 static std::atomic<int> g_knobs[16] = {{0}, {0}, {8}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}};
 int knob(int key) { return (key >= 0 && key < 16) ? g_knobs[key].load(std::memory_order_relaxed) : 0; }
+
+NvtxScope::NvtxScope(const char* name) : on(knob(15) != 0) {
+  if (on) nvtxRangePushA(name);
+}
 
 static thread_local char g_cuda_err[256] = "";
 
@@ -88,6 +104,7 @@ int b200awq_debug_read(void* host_dst, size_t bytes) {
 
 int b200awq_dequantize_gemm(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out_f16, int K,
                             int N, int group_size, b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_dequantize_gemm");
   const int G = group_size <= 0 ? K : group_size;
   if (!qweight || !scales || !qzeros || !out_f16 || !shape_ok(1, K, N, G)) return B200AWQ_EINVAL;
   return fold(dequantize_gemm(qweight, scales, qzeros, out_f16, K, N, G, static_cast<cudaStream_t>(stream)));
@@ -96,6 +113,7 @@ int b200awq_dequantize_gemm(const int32_t* qweight, const void* scales, const in
 int b200awq_gemm_forward(const void* x, int64_t ldx, const int32_t* qweight, const void* scales,
                          const int32_t* qzeros, const void* bias, void* y, int M, int K, int N, int group_size,
                          void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_gemm_forward");
   const int G = group_size <= 0 ? K : group_size;
   if (!shape_ok(M, K, N, G) || ldx < K) return B200AWQ_EINVAL;
   if (M == 0) return B200AWQ_OK;
@@ -116,6 +134,7 @@ int b200awq_gemm_forward(const void* x, int64_t ldx, const int32_t* qweight, con
 int b200awq_gemv_forward(const void* x, int64_t ldx, const int32_t* qweight, const void* scales,
                          const int32_t* qzeros, const void* bias, void* y, int M, int K, int N, int group_size,
                          void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_gemv_forward");
   const int G = group_size <= 0 ? K : group_size;
   if (!shape_ok(M, K, N, G) || ldx < K || (K % 32) != 0) return B200AWQ_EINVAL;
   if (G != 32 && G != 64 && G < 128) return B200AWQ_EUNSUPPORTED;  // calculate_zeros_width's domain
@@ -132,6 +151,7 @@ int b200awq_gemv_forward(const void* x, int64_t ldx, const int32_t* qweight, con
 int b200awq_fast_forward(const void* x, int64_t ldx, const int16_t* qweight, const void* scales,
                          const void* scaled_zeros, const void* bias, void* y, int M, int K, int N, int group_size,
                          void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_fast_forward");
   const int G = group_size <= 0 ? K : group_size;
   if (!shape_ok(M, K, N, G) || ldx < K || (K % 64) != 0 || (G % 32) != 0) return B200AWQ_EINVAL;
   if (M == 0) return B200AWQ_OK;
@@ -150,12 +170,14 @@ int b200awq_fast_forward(const void* x, int64_t ldx, const int16_t* qweight, con
 
 int b200awq_rmsnorm(const void* x, const void* weight, void* out, int rows, int hidden, float eps,
                     b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_rmsnorm");
   if (!x || !weight || !out || rows < 0 || hidden <= 0) return B200AWQ_EINVAL;
   if (rows == 0) return B200AWQ_OK;
   return fold(rmsnorm(x, weight, out, rows, hidden, eps, static_cast<cudaStream_t>(stream)));
 }
 
 int b200awq_silu_and_mul(const void* gate_up, void* out, int rows, int d, b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_silu_and_mul");
   if (!gate_up || !out || rows < 0 || d <= 0) return B200AWQ_EINVAL;
   if (rows == 0) return B200AWQ_OK;
   return fold(silu_and_mul(gate_up, out, rows, d, static_cast<cudaStream_t>(stream)));
@@ -188,6 +210,7 @@ size_t b200awq_stream_bytes(int K, int N, int group_size) {
 
 int b200awq_stream_pack(const int32_t* qweight, const void* scales, const int32_t* qzeros, void* out, int K, int N,
                         int group_size, int mode, b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_stream_pack");
   if (!qweight || !scales || !qzeros || !out) return B200AWQ_EINVAL;
   if (!shape_ok(1, K, N, group_size)) return B200AWQ_EINVAL;
   if (!stream_format_supported(K, N, group_size, mode)) return B200AWQ_EUNSUPPORTED;
@@ -195,6 +218,7 @@ int b200awq_stream_pack(const int32_t* qweight, const void* scales, const int32_
 }
 
 int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_program_run");
   if (prog == nullptr) return B200AWQ_EINVAL;
   Program* p = reinterpret_cast<Program*>(prog);
   if (program_is_stream(p)) return fold(program_run(p, nullptr, static_cast<cudaStream_t>(stream)));   // owns its rows
@@ -211,6 +235,7 @@ int b200awq_program_destroy(b200awq_program_t prog) {
 
 int b200awq_topk_softmax(const float* gating_output, float* topk_weights, int32_t* topk_ids,
                          int32_t* token_expert_indices, int M, int E, int topk, b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_topk_softmax");
   if (M < 0 || E <= 0 || topk <= 0 || topk > E) return B200AWQ_EINVAL;
   if (M == 0) return B200AWQ_OK;
   if (!gating_output || !topk_weights || !topk_ids || !token_expert_indices) return B200AWQ_EINVAL;
@@ -222,6 +247,7 @@ int b200awq_topk_softmax(const float* gating_output, float* topk_weights, int32_
 int b200awq_moe_align_block_size(const int32_t* topk_ids, int numel, int num_experts, int block_size,
                                  int32_t* sorted_ids, int32_t* expert_ids, int32_t* num_tokens_post_pad,
                                  b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_moe_align_block_size");
   if (numel < 0 || num_experts <= 0 || block_size <= 0) return B200AWQ_EINVAL;
   if (!topk_ids || !sorted_ids || !expert_ids || !num_tokens_post_pad) return B200AWQ_EINVAL;
   return fold(moe_align_block_size(topk_ids, numel, num_experts, block_size, sorted_ids, expert_ids, num_tokens_post_pad,
@@ -233,6 +259,7 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
                                  const int32_t* expert_ids, const int32_t* num_tokens_post_pad, void* y, int T, int topk,
                                  int sorted_len, int E, int K, int N, int group_size, int mul_weights, int block_size,
                                  void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_grouped_gemm_forward");
   const int G = group_size <= 0 ? K : group_size;
   if (T < 0 || topk <= 0 || sorted_len < 0 || E <= 0 || !shape_ok(1, K, N, G) || block_size <= 0) return B200AWQ_EINVAL;
   if (x_rows_per_token != 1 && x_rows_per_token != topk) return B200AWQ_EINVAL;

@@ -379,6 +379,101 @@ def prefill_leg(torch, rep_weights, dev, steps, peaks):
             "frac_of_burst_bf16_peak": round(tf / peaks["bf16_tflops"], 4), "kernel": "gemm_tc_kernel (tcgen05)"}
 
 
+# ------------------------------------------------------------- tensor-parallel leg (BASELINE config 5), N > 1 only
+L70 = {"hidden": 8192, "inter": 28672, "layers": 80, "heads": 64, "kv_heads": 8, "head_dim": 128}
+
+
+def tp70b_leg(torch, dist, rank, world, dev, steps, layers=None):
+    """Llama-3-70B-shaped decode step (bs = 1), tensor-parallel over the `world` GPUs of the box through
+    autoawq_b200/shard.py: fused q|k|v split by head group and gate|up split by column (no collective), o / down split
+    by row, ONE NCCL all-reduce of the fp16 [1, 8192] partial output after each of them - 160 all-reduces
+    of 16 KB per token, captured with the kernels in one CUDA graph.  Every rank builds the same full packed tensors
+    layer by layer (same seed), keeps its shard and drops the rest.  Attention / KV cache are not on the path: the
+    rank's q columns stand in for its attention output, as in the single-GPU step."""
+    from autoawq_b200 import ext, shard as S
+
+    c = dict(L70)
+    if layers:
+        c["layers"] = layers
+    H, I, G = c["hidden"], c["inter"], GROUP
+    qkv_n = (c["heads"] + 2 * c["kv_heads"]) * c["head_dim"]
+    if c["kv_heads"] % world or c["heads"] % world:
+        return {"unavailable": f"heads do not divide by {world}"}
+
+    def packed(K, N, gen):
+        qw = torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, device=dev, generator=gen)
+        qz = torch.randint(-2**31, 2**31 - 1, (K // G, N // 8), dtype=torch.int32, device=dev, generator=gen)
+        sc = ((torch.rand((K // G, N), device=dev, generator=gen) * 0.5 + 0.75) / (6.1 * K**0.5)).half()
+        return S.PackedGemm(qw, qz, sc)
+
+    ws, alg = [], 0
+    for l in range(c["layers"]):
+        gen = torch.Generator(device=dev).manual_seed(1000 + l)       # same full tensors on every rank
+        qkv = S.shard_qkv(packed(H, qkv_n, gen), c["heads"], c["kv_heads"], c["head_dim"], rank, world)
+        o = S.shard_rows(packed(H, H, gen), rank, world)
+        mlp = S.TensorParallelMLP(packed(H, I, gen), packed(H, I, gen), packed(I, H, gen), rank, world)
+        ws.append((qkv, o, mlp.gu, mlp.down))
+        if l == 0:
+            alg = sum(linear_bytes(p.in_features, p.out_features, 1) for p in ws[0])
+    torch.cuda.empty_cache()
+    q_local = c["heads"] // world * c["head_dim"]
+    nw = torch.ones(H, dtype=torch.float16, device=dev)
+    h0 = torch.randn((1, H), device=dev, dtype=torch.float16, generator=torch.Generator(device=dev).manual_seed(7))
+    xn = torch.empty((1, H), dtype=torch.float16, device=dev)
+    act = torch.empty((1, ws[0][3].in_features), dtype=torch.float16, device=dev)
+
+    def lin(x, p):
+        return ext.linear_forward("gemm", x, p.qweight, p.scales, p.qzeros, G)
+
+    def step(collectives=True):
+        h = h0
+        for qkv, o, gu, down in ws:
+            ext.layernorm_forward_cuda(h, nw, xn, 1e-5)
+            a = lin(xn, qkv)[:, :q_local]
+            y = lin(a, o)
+            if collectives:
+                dist.all_reduce(y)
+            ext.layernorm_forward_cuda(y, nw, xn, 1e-5)
+            g = lin(xn, gu)
+            ext.silu_and_mul(act, g)
+            h = lin(act, down)
+            if collectives:
+                dist.all_reduce(h)
+        return h
+
+    def ar_only():
+        for _ in range(2 * c["layers"]):
+            dist.all_reduce(xn)
+
+    dist.all_reduce(xn)            # communicator warm-up outside any capture
+    torch.cuda.synchronize()
+    out = {"workload": f"Llama-3-70B W4A16 g128 decode bs=1, tp={world}: {c['layers']} layers x [qkv {H}x{qkv_n // world}, "
+                       f"o {H // world}x{H} + all-reduce, gate|up {H}x{2 * I // world}, down {I // world}x{H} + all-reduce]",
+           "weights_gb_per_gpu": round(alg * c["layers"] / 1e9, 2), "collective": "NCCL all-reduce fp16 [1, 8192] (16 KB) x "
+           f"{2 * c['layers']} per token, inside the CUDA graph"}
+    res = {}
+    for name, fn in (("step", step), ("no_collective", lambda: step(False)), ("allreduce_only", ar_only)):
+        try:
+            g, _ = capture(torch, fn)
+            f = g.replay
+            graphed = True
+        except Exception as ex:  # noqa: BLE001
+            torch.cuda.synchronize()
+            f, graphed = fn, False
+            out.setdefault("notes", []).append(f"{name}: not captured ({type(ex).__name__}), timed eagerly")
+        sec = timed(torch, f, steps, 3, dist)
+        res[name] = (sec / steps, graphed)
+    t = res["step"][0]
+    out.update({"tok_s": round(1.0 / t, 2), "ms_per_step": round(t * 1e3, 4), "cuda_graph": res["step"][1],
+                "ms_per_step_without_collectives": round(res["no_collective"][0] * 1e3, 4),
+                "allreduce_us_each": round(res["allreduce_only"][0] / (2 * c["layers"]) * 1e6, 2),
+                "allreduce_ms_per_step": round(res["allreduce_only"][0] * 1e3, 4),
+                "per_gpu_gbs": round(alg * c["layers"] / t / 1e9, 1),
+                "per_gpu_frac_of_hbm_peak": round(alg * c["layers"] / t / 1e9 / measured_peaks()["hbm_gbs"], 4),
+                "limiter": "all-reduce latency" if res["allreduce_only"][0] > 0.5 * t else "weight streaming + launches"})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -393,6 +488,7 @@ def main():
                     help="decode: 1 = record the step once and run it as ONE persistent kernel (b200awq_program_*); "
                          "0 = one kernel launch per operator call")
     ap.add_argument("--layers", type=int, default=LAYERS, help="debug only: fewer layers => INVALID as a bench value")
+    ap.add_argument("--tp-layers", type=int, default=0, help="debug: layers of the tensor-parallel leg (0 = all 80)")
     ap.add_argument("--legs", type=int, default=1,
                     help="1: also run the secondary legs at N=1 (reference Triton on the same box, 4096x4096 GEMV, "
                          "prefill); 0: headline only")
@@ -591,6 +687,12 @@ def main():
             eager_ops = timed(torch, lambda: rep.step(rep.h), max(3, a.steps // 5), 2)
             config["per_op_eager_tok_s"] = round(max(3, a.steps // 5) / eager_ops, 1)
             config["prefill"] = prefill_leg(torch, rep.w, dev, a.steps, peaks)
+    # N > 1: the tensor-parallel leg (config 5); 35.6 GB / N of packed weights per GPU next to the replica's 7 GB
+    if world > 1 and a.legs and a.mode == "decode":
+        try:
+            config["tp70b"] = tp70b_leg(torch, dist, rank, world, dev, max(5, a.steps // 2), a.tp_layers)
+        except Exception as ex:  # noqa: BLE001
+            config["tp70b"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -143,6 +143,7 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *   key 12: 2 = grouped_gemm_forward always uses the register-staged grouped kernel
  *   key 13: decode program (read at b200awq_program_create): minimum tiles per participating CTA; ops with fewer
  *           tiles per CTA are shared by fewer CTAs (0 = every CTA takes part in every op, the default: measured best)
+ *   key 15: 1 = wrap every launching entry point in an NVTX range named after it (profiler timelines); default 0
  *   key 14: decode program kind (read at b200awq_program_create): 0 = stream variant when the sequence fits it,
  *           else the split-K kernel; 1 = split-K kernel only; 2 = stream variant only
  */
