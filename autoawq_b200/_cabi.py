@@ -69,6 +69,12 @@ SIGNATURES = {
         [_c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
          _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_size_t, _c_void_p],
     ),
+    "b200awq_comm_create": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_void_p)]),
+    "b200awq_comm_ipc_handle": (_c_int, [_c_void_p, _c_void_p]),
+    "b200awq_comm_open": (_c_int, [_c_void_p, _c_void_p]),
+    "b200awq_comm_all_reduce": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p]),
+    "b200awq_comm_error": (_c_int, [_c_void_p]),
+    "b200awq_comm_destroy": (_c_int, [_c_void_p]),
     "b200awq_program_create": (_c_int, [ctypes.POINTER(Op), _c_int, ctypes.POINTER(_c_void_p)]),
     "b200awq_program_num_ops": (_c_int, [_c_void_p]),
     "b200awq_program_kind": (_c_int, [_c_void_p]),

@@ -21,8 +21,8 @@ struct NvtxScope {
   }
 };
 
-static std::atomic<int> g_knobs[16] = {{0}, {0}, {8}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}, {0}};
-int knob(int key) { return (key >= 0 && key < 16) ? g_knobs[key].load(std::memory_order_relaxed) : 0; }
+static std::atomic<int> g_knobs[32] = {{0}, {0}, {8}};   // (the rest value-initialise to 0)
+int knob(int key) { return (key >= 0 && key < 32) ? g_knobs[key].load(std::memory_order_relaxed) : 0; }
 
 NvtxScope::NvtxScope(const char* name) : on(knob(15) != 0) {
   if (on) nvtxRangePushA(name);
@@ -89,8 +89,9 @@ size_t b200awq_workspace_bytes(int M, int K, int N) {
 }
 
 int b200awq_set_knob(int key, int value) {
-  if (key < 0 || key >= 16) return B200AWQ_EINVAL;
+  if (key < 0 || key >= 32) return B200AWQ_EINVAL;
   g_knobs[key].store(value, std::memory_order_relaxed);
+  if (key == 16) return fold(program_set_watchdog_seconds(value));   // decode-program watchdog (device-side constant)
   return B200AWQ_OK;
 }
 int b200awq_get_knob(int key) { return knob(key); }
@@ -230,6 +231,43 @@ int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspac
 
 int b200awq_program_destroy(b200awq_program_t prog) {
   program_destroy(reinterpret_cast<Program*>(prog));
+  return B200AWQ_OK;
+}
+
+int b200awq_comm_create(int rank, int world, int max_elems, b200awq_comm_t* out) {
+  if (out == nullptr) return B200AWQ_EINVAL;
+  Comm* c = nullptr;
+  cudaError_t ce = cudaSuccess;
+  const int rc = comm_create(rank, world, max_elems, &c, &ce);
+  if (rc == B200AWQ_ECUDA) return fold(ce);
+  if (rc != B200AWQ_OK) return rc;
+  *out = reinterpret_cast<b200awq_comm_t>(c);
+  return B200AWQ_OK;
+}
+int b200awq_comm_ipc_handle(b200awq_comm_t comm, void* out64) {
+  if (comm == nullptr || out64 == nullptr) return B200AWQ_EINVAL;
+  return fold(comm_ipc_handle(reinterpret_cast<Comm*>(comm), out64));
+}
+int b200awq_comm_open(b200awq_comm_t comm, const void* handles) {
+  if (comm == nullptr || handles == nullptr) return B200AWQ_EINVAL;
+  return fold(comm_open(reinterpret_cast<Comm*>(comm), handles));
+}
+int b200awq_comm_all_reduce(b200awq_comm_t comm, void* y, int n, b200awq_stream_t stream) {
+  NvtxScope nvtx_("b200awq_comm_all_reduce");
+  Comm* c = reinterpret_cast<Comm*>(comm);
+  if (c == nullptr || y == nullptr || n <= 0 || (n % 8) != 0 || (reinterpret_cast<uintptr_t>(y) & 15) != 0) return B200AWQ_EINVAL;
+  if (!comm_ready(c)) return B200AWQ_EINVAL;
+  if (n > comm_max_elems(c)) return B200AWQ_EUNSUPPORTED;
+  return fold(comm_all_reduce(c, y, n, static_cast<cudaStream_t>(stream)));
+}
+int b200awq_comm_error(b200awq_comm_t comm) {
+  if (comm == nullptr) return B200AWQ_EINVAL;
+  int f = 0;
+  const int rc = fold(comm_error_flag(reinterpret_cast<Comm*>(comm), &f));
+  return rc != B200AWQ_OK ? rc : (f != 0 ? B200AWQ_ECUDA : B200AWQ_OK);
+}
+int b200awq_comm_destroy(b200awq_comm_t comm) {
+  comm_destroy(reinterpret_cast<Comm*>(comm));
   return B200AWQ_OK;
 }
 

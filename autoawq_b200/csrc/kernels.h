@@ -94,6 +94,7 @@ void program_destroy(Program* p);
 cudaError_t program_debug_read(void* dst, size_t bytes);
 cudaError_t program_abort_read(void* dst, size_t bytes);
 cudaError_t stream_debug_read(void* dst, size_t bytes);
+cudaError_t program_set_watchdog_seconds(int seconds);
 
 // grouped persistent GEMV (gemv.cu): the decode-size path of grouped_gemm_forward
 bool gemv_v3_moe_supported(int K, int N, int G, int hbs);
@@ -112,6 +113,17 @@ cudaError_t moe_grouped_gemm(const void* x, int x_per_slot, const int32_t* qweig
                              const int32_t* qzeros, const float* topk_w, const int* sorted_ids, const int* expert_ids,
                              const int* num_post_pad, void* y, int n_slots, int topk, int sorted_len, int K, int N, int G,
                              int mul_weights, int block_size, cudaStream_t st);
+
+// one-shot all-reduce over peer memory (comm.cu)
+struct Comm;
+int comm_create(int rank, int world, int max_elems, Comm** out, cudaError_t* err);
+cudaError_t comm_ipc_handle(Comm* c, void* out64);
+cudaError_t comm_open(Comm* c, const void* handles);
+cudaError_t comm_all_reduce(Comm* c, void* y, int n, cudaStream_t st);
+bool comm_ready(const Comm* c);
+int comm_max_elems(const Comm* c);
+cudaError_t comm_error_flag(Comm* c, int* out);
+void comm_destroy(Comm* c);
 
 cudaError_t rmsnorm(const void* x, const void* w, void* out, int rows, int hidden, float eps, cudaStream_t st);
 cudaError_t silu_and_mul(const void* gate_up, void* out, int rows, int d, cudaStream_t st);

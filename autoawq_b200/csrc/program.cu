@@ -163,6 +163,13 @@ cudaError_t program_abort_clear(cudaStream_t st) {
   cudaError_t e = cudaGetSymbolAddress(&p, g_prog_abort);
   return e != cudaSuccess ? e : cudaMemsetAsync(p, 0, sizeof(g_prog_abort), st);
 }
+// watchdog limit in ns (default 0.5 s; knob 7 = seconds, for runs under compute-sanitizer / cuda-gdb where a kernel
+// is orders of magnitude slower and a healthy wait would be mistaken for a lost completion)
+__device__ unsigned long long g_prog_watch_ns = 500000000ull;
+cudaError_t program_set_watchdog_seconds(int seconds) {
+  const unsigned long long ns = seconds > 0 ? (unsigned long long)seconds * 1000000000ull : 500000000ull;
+  return cudaMemcpyToSymbol(g_prog_watch_ns, &ns, sizeof(ns));
+}
 struct ProgWatch {
   unsigned long long t_start = 0;
   int spins = 0;
@@ -176,7 +183,7 @@ struct ProgWatch {
       }
       const unsigned long long now = prog_timer();
       if (t_start == 0) t_start = now;
-      else if (now - t_start > 500000000ull) {
+      else if (now - t_start > g_prog_watch_ns) {
         if (atomicCAS(&g_prog_abort[3], 0, 1) == 0) {
           g_prog_abort[0] = code;
           g_prog_abort[1] = op;

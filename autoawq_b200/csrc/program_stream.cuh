@@ -69,6 +69,14 @@ __device__ __forceinline__ uint4 ld_relaxed_u4(const void* p) {
 __device__ __forceinline__ void st_relaxed_u32(void* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_release_cta_smem(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta_smem(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t sp_tag(int base, int op) { return (uint32_t)((base + op) % 65535 + 1); }
 
 // set -> original columns (oracle/stream_format.py:set_columns)
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(32 + NW * 32, 1)
   int* wfirst = misc + 8;                              // [NW] first local set each warp touched (-1: none)
   int* wlast = misc + 8 + NW;                    // [NW]
   uint32_t* scta = reinterpret_cast<uint32_t*>(misc + 8 + 2 * NW);   // [2][2] this CTA's unit range (with sdesc)
-  volatile int* staged_op = reinterpret_cast<volatile int*>(misc + 12 + 2 * NW);   // last op this CTA staged
+  int* staged_op = misc + 12 + 2 * NW;                 // last op this CTA staged (release / acquire at CTA scope)
   static_assert((13 + 2 * NW) * 4 <= 256, "misc area");
   uint32_t* xs = reinterpret_cast<uint32_t*>(sp_smem + sp_fixed_smem(NW, SPW));   // activations in B-fragment order
 
@@ -372,7 +380,7 @@ __global__ void __launch_bounds__(32 + NW * 32, 1)
         // ops).  A deep ring of bulk loads is also a deep queue on the SM's return path: every poll of the hand-off
         // waited behind ~100 KB of weight tiles (measured: 1.3 us per L2 round trip against 0.13 us unloaded).  While
         // the consumers hand over, the stream continues into L2 (prefetch cursor below), not into this SM.
-        if (active && op <= *staged_op + gate_ahead) {
+        if (active && (gate_ahead >= (1 << 20) || op <= ld_acquire_cta_smem(staged_op) + gate_ahead)) {
           const int stage = w * SPW + stage_i;
           if (mbar_test_wait(&empty[stage], ph ^ 1)) {
             const int n = (int)(cur.ub - cur.u) < cur.ups ? (int)(cur.ub - cur.u) : cur.ups;
@@ -577,7 +585,7 @@ __global__ void __launch_bounds__(32 + NW * 32, 1)
         }
         named_bar_sync_gv(1, (NW * 32));
       }
-      if (ct == 0) *staged_op = op;      // releases the producer's loads of this op (see the gate)
+      if (ct == 0) st_release_cta_smem(staged_op, op);      // releases the producer's loads of this op (see the gate)
       SP_STAMP(2);
       SP_TOUCH_SMEM();
       SP_WSTAMP(2);

@@ -117,10 +117,13 @@ class TensorParallelMLP:
     the tests.  gate / up are split on the boundaries of down's K split (its group size), so the activation width
     of a rank always equals its number of down rows, also when (I / G) % world != 0."""
 
-    def __init__(self, gate: PackedGemm, up: PackedGemm, down: PackedGemm, rank: int, world: int, group=None):
+    def __init__(self, gate: PackedGemm, up: PackedGemm, down: PackedGemm, rank: int, world: int, group=None,
+                 all_reduce=None):
+        """`all_reduce`: callable summing a tensor over the ranks in place (e.g. autoawq_b200.comm.OneShotAllReduce);
+        default: torch.distributed.all_reduce (NCCL on GPUs, gloo in the CPU tests)."""
         from . import ext
 
-        self.ext, self.group = ext, group
+        self.ext, self.group, self.all_reduce = ext, group, all_reduce
         quantum = max(8, down.group_size)
         g, u = shard_columns(gate, rank, world, quantum), shard_columns(up, rank, world, quantum)
         bias = None
@@ -144,4 +147,4 @@ class TensorParallelMLP:
         e.silu_and_mul(act, gu)
         y = e.linear_forward("gemm", act, self.down.qweight, self.down.scales, self.down.qzeros, self.down.group_size,
                              self.down.bias)
-        return all_reduce_sum(y, self.group)
+        return self.all_reduce(y) if self.all_reduce is not None else all_reduce_sum(y, self.group)

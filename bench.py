@@ -425,34 +425,39 @@ def tp70b_leg(torch, dist, rank, world, dev, steps, layers=None):
     def lin(x, p):
         return ext.linear_forward("gemm", x, p.qweight, p.scales, p.qzeros, G)
 
-    def step(collectives=True):
+    from autoawq_b200.comm import OneShotAllReduce
+
+    oneshot = OneShotAllReduce(max_elems=H)          # symmetric buffers + IPC handle exchange, once
+
+    def step(collective="nccl"):
+        ar = {"nccl": dist.all_reduce, "oneshot": oneshot, "none": lambda t: t}[collective]
         h = h0
         for qkv, o, gu, down in ws:
             ext.layernorm_forward_cuda(h, nw, xn, 1e-5)
             a = lin(xn, qkv)[:, :q_local]
             y = lin(a, o)
-            if collectives:
-                dist.all_reduce(y)
+            ar(y)
             ext.layernorm_forward_cuda(y, nw, xn, 1e-5)
             g = lin(xn, gu)
             ext.silu_and_mul(act, g)
             h = lin(act, down)
-            if collectives:
-                dist.all_reduce(h)
+            ar(h)
         return h
 
-    def ar_only():
+    def ar_only(collective="nccl"):
+        ar = dist.all_reduce if collective == "nccl" else oneshot
         for _ in range(2 * c["layers"]):
-            dist.all_reduce(xn)
+            ar(xn)
 
     dist.all_reduce(xn)            # communicator warm-up outside any capture
     torch.cuda.synchronize()
     out = {"workload": f"Llama-3-70B W4A16 g128 decode bs=1, tp={world}: {c['layers']} layers x [qkv {H}x{qkv_n // world}, "
                        f"o {H // world}x{H} + all-reduce, gate|up {H}x{2 * I // world}, down {I // world}x{H} + all-reduce]",
-           "weights_gb_per_gpu": round(alg * c["layers"] / 1e9, 2), "collective": "NCCL all-reduce fp16 [1, 8192] (16 KB) x "
-           f"{2 * c['layers']} per token, inside the CUDA graph"}
+           "weights_gb_per_gpu": round(alg * c["layers"] / 1e9, 2)}
     res = {}
-    for name, fn in (("step", step), ("no_collective", lambda: step(False)), ("allreduce_only", ar_only)):
+    for name, fn in (("step", lambda: step("oneshot")), ("step_nccl", lambda: step("nccl")),
+                     ("no_collective", lambda: step("none")), ("allreduce_only", lambda: ar_only("oneshot")),
+                     ("allreduce_only_nccl", lambda: ar_only("nccl"))):
         try:
             g, _ = capture(torch, fn)
             f = g.replay
@@ -463,8 +468,17 @@ def tp70b_leg(torch, dist, rank, world, dev, steps, layers=None):
             out.setdefault("notes", []).append(f"{name}: not captured ({type(ex).__name__}), timed eagerly")
         sec = timed(torch, f, steps, 3, dist)
         res[name] = (sec / steps, graphed)
+    oneshot.check()
+    # both collectives give the same sums up to the fp16 rounding of NCCL's own reduction order
+    y1, y2 = step("oneshot").float(), step("nccl").float()
+    torch.cuda.synchronize()
     t = res["step"][0]
     out.update({"tok_s": round(1.0 / t, 2), "ms_per_step": round(t * 1e3, 4), "cuda_graph": res["step"][1],
+                "collective": f"one-shot all-reduce over NVLink peer memory (csrc/comm.cu), fp16 [1, {H}] (16 KB) x "
+                              f"{2 * c['layers']} per token, one kernel each, inside the CUDA graph",
+                "nccl": {"tok_s": round(1.0 / res["step_nccl"][0], 2), "ms_per_step": round(res["step_nccl"][0] * 1e3, 4),
+                         "allreduce_us_each": round(res["allreduce_only_nccl"][0] / (2 * c["layers"]) * 1e6, 2)},
+                "max_abs_diff_vs_nccl": float((y1 - y2).abs().max()),
                 "ms_per_step_without_collectives": round(res["no_collective"][0] * 1e3, 4),
                 "allreduce_us_each": round(res["allreduce_only"][0] / (2 * c["layers"]) * 1e6, 2),
                 "allreduce_ms_per_step": round(res["allreduce_only"][0] * 1e3, 4),
@@ -542,15 +556,24 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback in the product path)")
     dist = None
+    nccl_log = None
     if world > 1:
         # NCCL's INFO log (communicator ranks, NVLS / ring choice) goes to STDERR: stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,GRAPH")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if "NCCL_DEBUG_FILE" not in os.environ:      # (a caller's own NCCL log settings win)
+            logdir = os.path.join(ROOT, "gpurun_out") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "/tmp"
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(logdir, "nccl_bench.%h.%p.log")
+            nccl_log = os.path.join(logdir, f"nccl_bench.{os.uname().nodename}.{os.getpid()}.log")
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        if rank == 0 and nccl_log and os.path.exists(nccl_log):      # the communicator's own words, on stderr
+            for ln in open(nccl_log, errors="replace"):
+                if "nranks" in ln or "NVLS" in ln or "Connected" in ln:
+                    print(ln.rstrip(), file=sys.stderr)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     rep = Replica(dev, M, layers=a.layers, seed=rank)

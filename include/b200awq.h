@@ -143,6 +143,8 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *   key 12: 2 = grouped_gemm_forward always uses the register-staged grouped kernel
  *   key 13: decode program (read at b200awq_program_create): minimum tiles per participating CTA; ops with fewer
  *           tiles per CTA are shared by fewer CTAs (0 = every CTA takes part in every op, the default: measured best)
+ *   key 16: decode-program watchdog in seconds (0 = the default 0.5 s): every spin of the program kernels gives up
+ *           after this long; raise it under compute-sanitizer / a debugger, where kernels run orders of magnitude slower
  *   key 15: 1 = wrap every launching entry point in an NVTX range named after it (profiler timelines); default 0
  *   key 14: decode program kind (read at b200awq_program_create): 0 = stream variant when the sequence fits it,
  *           else the split-K kernel; 1 = split-K kernel only; 2 = stream variant only
@@ -201,6 +203,24 @@ int b200awq_program_num_ops(b200awq_program_t prog);
  * packed split-K sums; zero-initialised and left all-zero like the per-op workspace (the same buffer may serve both) */
 int b200awq_program_run(b200awq_program_t prog, void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
 int b200awq_program_destroy(b200awq_program_t prog);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * One-shot all-reduce over NVLink peer memory (csrc/comm.cu; SURVEY 8e: the reference has no collective at all -
+ * multi-GPU there is accelerate layer placement, awq/models/base.py:527-535).  For the tensor-parallel decode path:
+ * the fp16 partial outputs of a row-parallel linear (o_proj / down_proj split along K) are summed across the GPUs
+ * of one box in ONE kernel launch per call: push into every rank's inbox (P2P stores), flag, wait, reduce in rank
+ * order (bit-identical results on all ranks).  One process per GPU: create -> exchange the 64-byte IPC handles by
+ * any means (autoawq_b200/comm.py uses torch.distributed.all_gather_object) -> open -> all_reduce any number of
+ * times (asynchronous on `stream`, CUDA-graph capturable: the call counter lives on the device).  n % 8 == 0,
+ * n <= max_elems (larger messages: use NCCL), world <= 8, y 16-byte aligned; in place.  b200awq_comm_error
+ * synchronises and returns B200AWQ_ECUDA if a wait ever timed out (2 s: dead peer). */
+typedef struct b200awq_comm* b200awq_comm_t;
+int b200awq_comm_create(int rank, int world, int max_elems, b200awq_comm_t* out);
+int b200awq_comm_ipc_handle(b200awq_comm_t comm, void* out_64_bytes);
+int b200awq_comm_open(b200awq_comm_t comm, const void* handles_world_x_64_bytes);
+int b200awq_comm_all_reduce(b200awq_comm_t comm, void* y_f16, int n, b200awq_stream_t stream);
+int b200awq_comm_error(b200awq_comm_t comm);
+int b200awq_comm_destroy(b200awq_comm_t comm);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Stream format: the one-time, load-time re-layout of a GEMM-layout linear that the decode-program kernel

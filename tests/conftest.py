@@ -32,3 +32,21 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _program_watchdog_for_sanitizer_runs():
+    """B200AWQ_WATCHDOG_S=<seconds> (tools/sanitize.sh): lengthen the decode-program kernels' spin watchdog
+    (knob 16) - under compute-sanitizer a healthy wait takes longer than the default 0.5 s."""
+    secs = os.environ.get("B200AWQ_WATCHDOG_S")
+    if secs:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                from autoawq_b200 import ext
+
+                ext.set_knob(16, int(secs))
+        except Exception:  # noqa: BLE001
+            pass
+    yield

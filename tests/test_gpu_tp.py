@@ -51,6 +51,41 @@ def _worker(rank, world, port, ret):
             # two fp16 roundings upstream + fp16 partial sums reduced across ranks
             tol = 4e-3 * np.abs(ref) + 2e-3 * np.sqrt(np.mean(ref**2)) + 1e-4
             assert np.all(np.abs(y - ref) <= tol), f"rank {rank} M={M}: max err {np.abs(y - ref).max()}"
+        # ---- the one-shot all-reduce over peer memory (csrc/comm.cu) against the sum of the gathered partials
+        from autoawq_b200.comm import OneShotAllReduce
+
+        ar = OneShotAllReduce(max_elems=8192)
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        for it, n in enumerate([8192, 4096, 8, 8192, 8192]):       # several calls: both parities, reuse
+            part = torch.randn(n, device=dev, dtype=torch.float16, generator=g)
+            parts = [torch.empty_like(part) for _ in range(world)]
+            dist.all_gather(parts, part)
+            want = sum(p.float() for p in parts).half()            # rank order, fp32 accumulation, one rounding
+            got = ar(part.clone())
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), f"rank {rank} call {it}: one-shot all-reduce differs from the rank-ordered sum"
+        # inside a CUDA graph, replayed: the call counter lives on the device
+        buf = torch.zeros(8192, device=dev, dtype=torch.float16)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            ar(buf)
+            s.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                ar(buf)
+            for rep in range(5):
+                buf.fill_(float(rank + 1 + rep))
+                gr.replay()
+                s.synchronize()
+                assert float(buf[0]) == sum(r + 1 + rep for r in range(world)), f"rank {rank} replay {rep}"
+        ar.check()
+        # the tensor-parallel MLP with the one-shot collective gives the same result as with NCCL (same partials;
+        # NCCL's reduction order may differ in the last bit)
+        mlp1 = S.TensorParallelMLP(packed(cg), packed(cu), packed(cd), rank, world, all_reduce=ar)
+        x = torch.from_numpy((np.random.default_rng(5).standard_normal((1, K)) * 0.5).astype(np.float16)).to(dev)
+        ya, yb = mlp1(x).float(), mlp(x).float()
+        assert torch.allclose(ya, yb, rtol=2e-3, atol=2e-3)
         ret[rank] = True
     finally:
         dist.destroy_process_group()
