@@ -361,8 +361,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   uint8_t* ring = v3_smem;                                   // NS x 8 KB weight tiles (1 KB aligned: swizzle atoms)
   uint8_t* aux = v3_smem + (size_t)NS * kV3TileBytes;        // NS x (256 scales + 32 zero words)
   float* red = reinterpret_cast<float*>(aux + (size_t)NS * kV3AuxBytes);
-  float* colacc = red + V3Smem<MT, SPW>::red_floats;
-  uint64_t* full = reinterpret_cast<uint64_t*>(colacc + V3Smem<MT, SPW>::colacc_floats);
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + V3Smem<MT, SPW>::red_floats);
   uint64_t* empty = full + NS;
   int* flags = reinterpret_cast<int*>(empty + NS);   // [0..7] per-warp push flags, [8] CTA flag,
   int* warp_cb = flags + 16;                         // [8] column block of each warp's pending sums
@@ -390,7 +389,6 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     }
     fence_mbar_init();
   }
-  for (int i = tid; i < V3Smem<MT, SPW>::colacc_floats; i += kV3Threads) colacc[i] = 0.f;
   __syncthreads();
   if (MOE) {
     bool any = false;
@@ -463,7 +461,11 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     scat.tw = moe.topk_w;
   }
   float* my_red = red + (size_t)cw * MT * kGvRedStride;
-  float* my_col = colacc + (size_t)cw * MT * kV3TileCols;
+  float ycol[MT][8];          // this lane's folded column sums: word-column `lane` (8 columns) x MT tokens
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ycol[m][j] = 0.f;
   const int a_w = t0 + (int)((int64_t)ntile * cw / kV3Warps);
   const int b_w = t0 + (int)((int64_t)ntile * (cw + 1) / kV3Warps);
 
@@ -529,8 +531,8 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     if (cb != cur_cb) {
       if (cur_cb >= 0 && ntl > 0) {
         // this warp's run crosses a column block: push its pending sums alone (rare)
-        __syncwarp();
-        v3_push_warp<MT>(my_col, cur_cb, ntl, TPC, lane, bias, y, acc_ws, tickets, M, N, scat);
+        v3_dump_cols<MT>(my_red, ycol, lane);
+        v3_push_warp<MT>(my_red, cur_cb, ntl, TPC, lane, bias, y, acc_ws, tickets, M, N, scat);
       }
       cur_cb = cb;
       ntl = 0;
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
     // ---- fold when the quantisation group (or this warp's run) ends with this tile -----------------
     const bool group_end = g_shift < 31 ? ((((kt + 1) * kV3TileRows) & (G - 1)) == 0) : (kt + 1 == TPC);
     if (group_end || t + 1 == b_w) {
-      v3_fold<MT>(sa, my_red, my_col, lane, g, tig, acc, xs_acc);
+      v3_fold_reg<MT>(sa, my_red, ycol, lane, g, tig, acc, xs_acc);
       zero_acc();
     }
     __syncwarp();
@@ -563,6 +565,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
 
   // ---- CTA-level reduction of the per-warp column sums, grouped by column block --------------------
   if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 3] = gtimer();
+  v3_dump_cols<MT>(my_red, ycol, lane);   // the staging area now carries the warp's column sums [MT][256]
   if (lane == 0) {
     warp_cb[cw] = (ntl > 0) ? cur_cb : -1;
     warp_ntl[cw] = ntl;
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       int w1 = w0 + 1;
       while (w1 < kV3Warps && warp_cb[w1] == cbg) ++w1;
       if (cbg >= 0)
-        v3_add_cols<MT, kV3Warps * 32>(colacc + (size_t)w0 * MT * kV3TileCols, w1 - w0, MT * kV3TileCols, cbg, ct, acc_ws,
+        v3_add_cols<MT, kV3Warps * 32>(red + (size_t)w0 * MT * kGvRedStride, w1 - w0, MT * kGvRedStride, cbg, ct, acc_ws,
                                        M, N, scat);
       w0 = w1;
     }
@@ -695,7 +698,7 @@ cudaError_t gemv_v3_moe(const void* x, int x_per_slot, const int32_t* qweight, c
   if (tokens <= 1) return go(gemv_v3_kernel<1, 3, false, true>, V3Smem<1, 3>::bytes, 1);
   if (tokens <= 2) return go(gemv_v3_kernel<2, 2, false, true>, V3Smem<2, 2>::bytes, 2);
   if (tokens <= 4) return go(gemv_v3_kernel<4, 2, false, true>, V3Smem<4, 2>::bytes, 4);
-  return go(gemv_v3_kernel<8, 1, false, true>, V3Smem<8, 1>::bytes, 8);
+  return go(gemv_v3_kernel<8, 2, false, true>, V3Smem<8, 2>::bytes, 8);
 }
 
 bool gemv_v3_moe_supported(int K, int N, int G, int hbs) {
@@ -726,7 +729,7 @@ cudaError_t gemv_v3(const GemmArgs& a, float* acc_ws, int* tickets, cudaStream_t
     return launch_v3<2, 2, false>(a, acc_ws, tickets, st);
   }
   if (a.M <= 4) return launch_v3<4, 2, false>(a, acc_ws, tickets, st);
-  return launch_v3<8, 1, false>(a, acc_ws, tickets, st);
+  return launch_v3<8, 2, false>(a, acc_ws, tickets, st);   // (column sums in registers: two ring stages also at MT = 8)
 }
 
 }  // namespace b200awq

@@ -40,10 +40,10 @@ struct V3Smem {
   // M <= 2, the staged activations)
   static constexpr int kStagesPerWarp = SPW;
   static constexpr int kStages = kV3Warps * kStagesPerWarp;
-  static constexpr int red_floats = kV3Warps * MT * kGvRedStride;    // per-warp raw sums [MT][288]
-  static constexpr int colacc_floats = kV3Warps * MT * kV3TileCols;  // per-warp column sums [MT][256]
-  static constexpr size_t bytes = (size_t)kStages * (kV3TileBytes + kV3AuxBytes) +
-                                  (size_t)(red_floats + colacc_floats) * 4 + 2 * kStages * 8 + 128;
+  static constexpr int red_floats = kV3Warps * MT * kGvRedStride;    // per-warp raw sums [MT][288]; at the end of a
+                                                                     // run the same area carries the warp's column sums
+  static constexpr size_t bytes = (size_t)kStages * (kV3TileBytes + kV3AuxBytes) + (size_t)red_floats * 4 +
+                                  2 * kStages * 8 + 128;
 };
 
 // Shared by the warp-level (NT = 32) and CTA-level (NT = 256) pushes: add `cols` [MT][256] (shared memory,
@@ -213,6 +213,80 @@ __device__ __forceinline__ void v3_fold(const uint8_t* sa, float* my_red, float*
       c0[1] = a1;
     }
   }
+}
+
+// As v3_fold, but the folded column sums stay in REGISTERS: lane l owns word-column l = 8 columns x MT tokens
+// (ycol[m][j]).  The per-warp column accumulators in shared memory cost 8 KB x MT per CTA - with MT = 8 that left room
+// for ONE ring stage per warp and the M = 8 GEMV ran 2.2x slower than M = 1 (19.9 vs 8.8 us on 4096 x 4096,
+// profiles/r02_m_sweep.json); in registers every MT gets at least two stages.
+template <int MT>
+__device__ __forceinline__ void v3_fold_reg(const uint8_t* sa, float* my_red, float (&ycol)[MT][8], int lane, int g, int tig,
+                                            const float (&acc)[4][4][4], const float (&xs_acc)[4]) {
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+#pragma unroll
+    for (int tt = 0; tt < 4; ++tt) {
+      const int pc = gv_pos(32 * g + 8 * w + 2 * tt);
+      if (2 * tig < MT)
+        *reinterpret_cast<float2*>(&my_red[(2 * tig) * kGvRedStride + pc]) = make_float2(acc[w][tt][0], acc[w][tt][2]);
+      if (2 * tig + 1 < MT)
+        *reinterpret_cast<float2*>(&my_red[(2 * tig + 1) * kGvRedStride + pc]) =
+            make_float2(acc[w][tt][1], acc[w][tt][3]);
+    }
+  float X[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    const float v = (m & 1) ? xs_acc[1] : xs_acc[0];
+    X[m] = __shfl_sync(0xffffffffu, v, m >> 1);
+  }
+  __syncwarp();
+  const uint4 sc4 = *reinterpret_cast<const uint4*>(sa + lane * 16);
+  const uint32_t zw = *reinterpret_cast<const uint32_t*>(sa + kV3ScaleBytes + lane * 4);
+  const __half2* sc2 = reinterpret_cast<const __half2*>(&sc4);
+  float sc[8], zoff[8];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const float2 f = __half22float2(sc2[jj]);
+    sc[2 * jj] = f.x;
+    sc[2 * jj + 1] = f.y;
+  }
+#pragma unroll
+  for (int jc = 0; jc < 8; ++jc) {
+    const int zshift = 4 * ((jc >> 1) + 4 * (jc & 1));
+    const float z = static_cast<float>((zw >> zshift) & 0xFu);
+    const bool kindB = ((jc >> 1) & 1) != 0;
+    zoff[jc] = kindB ? 1024.f + 16.f * z : 1024.f + z;
+    if (kindB) sc[jc] *= 0.0625f;
+  }
+  const int pc0 = gv_pos(8 * lane);
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    const float4 s0 = *reinterpret_cast<const float4*>(&my_red[m * kGvRedStride + pc0]);
+    const float4 s1 = *reinterpret_cast<const float4*>(&my_red[m * kGvRedStride + pc0 + 4]);
+    ycol[m][0] += sc[0] * (s0.x - zoff[0] * X[m]);
+    ycol[m][1] += sc[1] * (s0.y - zoff[1] * X[m]);
+    ycol[m][2] += sc[2] * (s0.z - zoff[2] * X[m]);
+    ycol[m][3] += sc[3] * (s0.w - zoff[3] * X[m]);
+    ycol[m][4] += sc[4] * (s1.x - zoff[4] * X[m]);
+    ycol[m][5] += sc[5] * (s1.y - zoff[5] * X[m]);
+    ycol[m][6] += sc[6] * (s1.z - zoff[6] * X[m]);
+    ycol[m][7] += sc[7] * (s1.w - zoff[7] * X[m]);
+  }
+  __syncwarp();   // the staging area may be rewritten (next fold, or the warp's column-sum dump)
+}
+// Dump the warp's column sums into its staging area as [MT][256] (the layout v3_add_cols / v3_push_warp read) and
+// clear them.
+template <int MT>
+__device__ __forceinline__ void v3_dump_cols(float* my_red, float (&ycol)[MT][8], int lane) {
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    *reinterpret_cast<float4*>(&my_red[m * kV3TileCols + 8 * lane]) = make_float4(ycol[m][0], ycol[m][1], ycol[m][2], ycol[m][3]);
+    *reinterpret_cast<float4*>(&my_red[m * kV3TileCols + 8 * lane + 4]) =
+        make_float4(ycol[m][4], ycol[m][5], ycol[m][6], ycol[m][7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ycol[m][j] = 0.f;
+  }
+  __syncwarp();
 }
 
 }  // namespace b200awq
