@@ -11,6 +11,7 @@
 // The cross-thread / cross-CTA (split-K) reduction is fp32; the result is rounded to fp16 once.
 #include <cuda.h>
 
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -628,6 +629,7 @@ struct NextW {
   long long bytes;
 };
 static NextW learn_successor(const void* w, long long bytes) {
+  if (knob(6) == 0) return NextW{nullptr, 0};   // (the default: no lock, no table on the launch path)
   static std::mutex mu;
   static std::unordered_map<const void*, NextW> succ;
   static const void* prev = nullptr;
@@ -638,6 +640,21 @@ static NextW learn_successor(const void* w, long long bytes) {
   auto it = succ.find(w);
   if (it == succ.end() || knob(6) == 0) return NextW{nullptr, 0};
   return it->second;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every launch (it is a
+// driver call of a few microseconds; the per-op path makes 160 launches per token).  `done` is one word per kernel
+// instantiation (a function-local static at the call site), bit d = device d.
+template <typename Kern>
+static cudaError_t ensure_smem_attr(Kern kern, size_t smem, std::atomic<uint64_t>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
 }
 
 template <int MT, int SPW, bool XS>
@@ -655,7 +672,9 @@ static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cud
   if (e != cudaSuccess) return e;
   auto kern = gemv_v3_kernel<MT, SPW, XS>;
   const size_t smem = V3Smem<MT, SPW>::bytes + (XS ? (size_t)MT * (a.K + 8) * 2 : 0);
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static std::atomic<uint64_t> attr_done{0};
+  // (XS variants size their request by K: set the maximum once, launch with the exact size)
+  e = ensure_smem_attr(kern, XS ? (size_t)227 * 1024 : smem, attr_done);
   if (e != cudaSuccess) return e;
   const int T = (a.N / kV3TileCols) * (a.K / kV3TileRows);
   const int grid = T < v3_sm_count() ? T : v3_sm_count();

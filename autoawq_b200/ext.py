@@ -22,6 +22,7 @@ __all__ = [
 
 _WS: dict = {}
 _WS_MIN = 16 << 20
+_WS_TICKETS = 16384          # kTicketBytes (csrc/kernels.h); tests/test_host_cpu.py checks it against the ABI
 
 
 def _require_cuda(*tensors):
@@ -80,27 +81,60 @@ def _check_w(t: torch.Tensor, dtype, name: str):
         raise B200AwqError(f"b200awq: {name} must be contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
 
 
-def linear_forward(layout: str, x, qweight, scales, qzeros, group_size: int, bias=None, out=None) -> torch.Tensor:
-    """Y = X . deq(W) (+ bias) for layout in {"gemm", "gemv", "fast"}; returns [M, N] fp16 (written into `out`
-    when given: a contiguous [M, N] fp16 tensor)."""
-    _require_cuda(x, qweight, scales, qzeros, bias)
+_LAYOUT = {
+    "gemm": (lib.b200awq_gemm_forward, torch.int32),
+    "gemv": (lib.b200awq_gemv_forward, torch.int32),
+    "fast": (lib.b200awq_fast_forward, torch.int16),
+}
+# validated weight triples: id(qweight) -> (weakref to qweight, data_ptrs, K, N, device).  A decode loop calls the
+# same 160 linears every token: dtype / contiguity / device checks and the pointer reads are done once per tensor
+# (the weakref guards against id() reuse after the tensor died; in-place updates keep the pointers valid).
+_WCACHE: dict = {}
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
+def _weights(layout: str, qweight, scales, qzeros):
+    import weakref
+
+    key = (id(qweight), id(scales), id(qzeros))
+    hit = _WCACHE.get(key)
+    if hit is not None and hit[0]() is qweight and hit[1] == qweight.data_ptr():
+        return hit
+    _require_cuda(qweight, scales, qzeros)
+    wdt = _LAYOUT[layout][1]
     if layout == "gemm":
         K, N = qweight.shape[0], qweight.shape[1] * 8
-        fn, wdt = lib.b200awq_gemm_forward, torch.int32
     elif layout == "gemv":
         N, K = qweight.shape[0], qweight.shape[1] * 8
-        fn, wdt = lib.b200awq_gemv_forward, torch.int32
-    elif layout == "fast":
-        N, K = qweight.shape[0] * 4, qweight.shape[1]
-        fn, wdt = lib.b200awq_fast_forward, torch.int16
     else:
-        raise ValueError(layout)
+        N, K = qweight.shape[0] * 4, qweight.shape[1]
     _check_w(qweight, wdt, "qweight")
     _check_w(scales, torch.float16, "scales")
     _check_w(qzeros, torch.float16 if layout == "fast" else torch.int32, "qzeros")
+    ent = (weakref.ref(qweight), qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(), K, N, qweight.device)
+    if len(_WCACHE) > 16384:
+        _WCACHE.clear()
+    _WCACHE[key] = ent
+    return ent
+
+
+def linear_forward(layout: str, x, qweight, scales, qzeros, group_size: int, bias=None, out=None) -> torch.Tensor:
+    """Y = X . deq(W) (+ bias) for layout in {"gemm", "gemv", "fast"}; returns [M, N] fp16 (written into `out`
+    when given: a contiguous [M, N] fp16 tensor).  The hot call of an eager decode loop (160 per token): weights are
+    validated once per tensor, no context-manager object, no extra ABI call (b200awq_workspace_bytes is
+    16384 + min(M, 64) * N * 4, restated here)."""
+    try:
+        fn = _LAYOUT[layout][0]
+    except KeyError:
+        raise ValueError(layout) from None
+    _, p_qw, p_sc, p_qz, K, N, dev = _weights(layout, qweight, scales, qzeros)
+    if not x.is_cuda or (bias is not None and not bias.is_cuda):
+        raise B200AwqError("b200awq: tensors must live on a CUDA device (there is no CPU path)")
     x2 = _x2d(x, K)
     M = x2.shape[0]
-    dev = x2.device
+    if x2.device != dev:
+        raise B200AwqError(f"b200awq: activations on {x2.device}, weights on {dev}")
     if out is None:
         y = torch.empty((M, N), dtype=torch.float16, device=dev)
     else:
@@ -110,15 +144,24 @@ def linear_forward(layout: str, x, qweight, scales, qzeros, group_size: int, bia
     if M == 0:
         return y
     G = K if group_size in (-1, 0) else int(group_size)
-    with _DeviceGuard(dev):
-        st = _stream(dev)
-        need = lib.b200awq_workspace_bytes(M, K, N)
-        ws = _workspace(dev, st, need)
-        ldx = x2.stride(0) if M > 1 else K
-        code = fn(x2.data_ptr(), ldx, qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(),
+    di = dev.index
+    cur = _cur_device() if _cur_device is not None else torch.cuda.current_device()
+    if cur != di:
+        torch.cuda.set_device(di)
+    try:
+        st = _raw_stream(di) if _raw_stream is not None else torch.cuda.current_stream(dev).cuda_stream
+        need = _WS_TICKETS + (M if M < 64 else 64) * N * 4
+        ws = _WS.get((di, st))
+        if ws is None or ws.numel() < need:
+            ws = _workspace(dev, st, need)
+        code = fn(x2.data_ptr(), x2.stride(0) if M > 1 else K, p_qw, p_sc, p_qz,
                   bias.data_ptr() if bias is not None else None, y.data_ptr(), M, K, N, G,
                   ws.data_ptr(), ws.numel(), st)
-    check(code, f"b200awq_{layout}_forward(M={M}, K={K}, N={N}, G={G})")
+    finally:
+        if cur != di:
+            torch.cuda.set_device(cur)
+    if code != 0:
+        check(code, f"b200awq_{layout}_forward(M={M}, K={K}, N={N}, G={G})")
     return y
 
 

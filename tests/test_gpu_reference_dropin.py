@@ -379,3 +379,48 @@ def test_reference_from_quantized_unfused(ref, tmp_path):
         a1 = model.model(ids[:, :1]).logits.float()
         b1 = twin(ids[:, :1]).logits.float()
     assert (a1 - b1).abs().max().item() <= 3e-2 * b1.abs().max().item() + 2e-2
+
+
+def test_reference_fused_topk_both_branches_agree(ref, monkeypatch):
+    """The reference itself holds a second definition of `topk_softmax`: on ROCm `fused_topk` computes
+    `torch.softmax` + `torch.topk` instead of calling the extension (awq/modules/fused/moe.py:150-153).  Running the
+    reference's own function through both branches - the extension branch lands in OUR awq_ext.topk_softmax - pins
+    the operator to reference code rather than to this repository's reading of it.  Same for the renormalisation."""
+    import awq.modules.fused.moe as M
+
+    rng = np.random.default_rng(12)
+    for (T, E, topk) in [(1, 8, 2), (7, 8, 2), (33, 64, 6), (5, 60, 4)]:
+        logits = torch.from_numpy(rng.standard_normal((T, E)).astype(np.float32)).to(_dev())
+        w_ext, id_ext = M.fused_topk(logits, topk, renormalize=True)
+        monkeypatch.setattr(torch.version, "hip", "reference-rocm-branch", raising=False)
+        try:
+            w_ref, id_ref = M.fused_topk(logits, topk, renormalize=True)
+        finally:
+            monkeypatch.setattr(torch.version, "hip", None, raising=False)
+        assert torch.equal(id_ext.long(), id_ref.long()), (T, E, topk)
+        assert torch.allclose(w_ext, w_ref, rtol=1e-5, atol=1e-7)
+
+
+def test_reference_moe_align_block_size_invariants(ref):
+    """moe_align_block_size through the reference's wrapper (moe.py:92-134), at sizes beyond its docstring example:
+    every expert's run is a multiple of the block, holds exactly that expert's slots in ascending order, padding slots
+    carry `numel`, expert_ids name the run's expert."""
+    import awq.modules.fused.moe as M
+
+    rng = np.random.default_rng(13)
+    for (T, E, topk, block) in [(4, 4, 3, 4), (1, 8, 2, 16), (37, 8, 2, 16), (100, 60, 4, 16)]:
+        ids = np.stack([rng.permutation(E)[:topk] for _ in range(T)]).astype(np.int32)
+        s_ids, e_ids, npost = M.moe_align_block_size(torch.from_numpy(ids).to(_dev()), block, E)
+        n = int(npost.item())
+        s_ids, e_ids = s_ids.cpu().numpy()[:n], e_ids.cpu().numpy()[: n // block]
+        assert n % block == 0
+        flat = ids.reshape(-1)
+        pos = 0
+        for e in range(E):
+            mine = np.where(flat == e)[0]
+            run = (len(mine) + block - 1) // block * block
+            assert np.array_equal(s_ids[pos:pos + len(mine)], mine), (T, E, e)
+            assert np.all(s_ids[pos + len(mine):pos + run] == flat.size)
+            assert np.all(e_ids[pos // block:(pos + run) // block] == e)
+            pos += run
+        assert pos == n

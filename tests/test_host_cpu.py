@@ -257,3 +257,32 @@ def test_decode_program_recorder_refuses_cpu_tensors(built):
         p.build()          # empty program
     with pytest.raises(B200AwqError):
         p.run()            # not built
+
+
+def test_python_workspace_size_restates_the_abi(built):
+    """ext.linear_forward sizes the split-K workspace without an extra ABI call; the restated formula must agree
+    with b200awq_workspace_bytes for every M."""
+    from autoawq_b200 import ext
+    from autoawq_b200._cabi import lib
+
+    for M in (1, 8, 63, 64, 65, 4096):
+        for N in (8, 4096, 28672):
+            assert lib.b200awq_workspace_bytes(M, 4096, N) == ext._WS_TICKETS + min(M, 64) * N * 4
+
+
+def test_comm_and_stream_argument_validation_without_gpu(built):
+    """The round-2 entry points reject bad arguments before touching a device."""
+    import ctypes
+
+    from autoawq_b200._cabi import lib
+
+    h = ctypes.c_void_p()
+    assert lib.b200awq_comm_create(0, 9, 8192, ctypes.byref(h)) == 1       # world > 8
+    assert lib.b200awq_comm_create(2, 2, 8192, ctypes.byref(h)) == 1       # rank out of range
+    assert lib.b200awq_comm_create(0, 2, 100, ctypes.byref(h)) == 1        # max_elems % 8
+    assert lib.b200awq_comm_all_reduce(None, None, 8, None) == 1
+    assert lib.b200awq_stream_bytes(4096, 4096, 128) == (4096 // 16) * (4096 // 128) * 1072
+    assert lib.b200awq_stream_bytes(4096, 4100, 128) == 0                  # N % 16
+    assert lib.b200awq_stream_bytes(4000, 4096, 32) == 0                   # K % 128
+    assert lib.b200awq_stream_pack(None, None, None, None, 4096, 4096, 128, 0, None) == 1
+    assert lib.b200awq_program_kind(None) == 0
