@@ -99,8 +99,11 @@ def _weights(layout: str, qweight, scales, qzeros):
 
     key = (id(qweight), id(scales), id(qzeros))
     hit = _WCACHE.get(key)
-    if hit is not None and hit[0]() is qweight and hit[1] == qweight.data_ptr():
-        return hit
+    if hit is not None:
+        refs = hit[7]
+        # ids are only unique among LIVE objects: every one of the three must still be the tensor that was validated
+        if refs[0]() is qweight and refs[1]() is scales and refs[2]() is qzeros and hit[1] == qweight.data_ptr():
+            return hit
     _require_cuda(qweight, scales, qzeros)
     wdt = _LAYOUT[layout][1]
     if layout == "gemm":
@@ -112,7 +115,10 @@ def _weights(layout: str, qweight, scales, qzeros):
     _check_w(qweight, wdt, "qweight")
     _check_w(scales, torch.float16, "scales")
     _check_w(qzeros, torch.float16 if layout == "fast" else torch.int32, "qzeros")
-    ent = (weakref.ref(qweight), qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(), K, N, qweight.device)
+    if scales.device != qweight.device or qzeros.device != qweight.device:
+        raise B200AwqError("b200awq: qweight / scales / qzeros must live on one device")
+    refs = (weakref.ref(qweight), weakref.ref(scales), weakref.ref(qzeros))
+    ent = (refs[0], qweight.data_ptr(), scales.data_ptr(), qzeros.data_ptr(), K, N, qweight.device, refs)
     if len(_WCACHE) > 16384:
         _WCACHE.clear()
     _WCACHE[key] = ent
@@ -128,7 +134,7 @@ def linear_forward(layout: str, x, qweight, scales, qzeros, group_size: int, bia
         fn = _LAYOUT[layout][0]
     except KeyError:
         raise ValueError(layout) from None
-    _, p_qw, p_sc, p_qz, K, N, dev = _weights(layout, qweight, scales, qzeros)
+    _, p_qw, p_sc, p_qz, K, N, dev, _refs = _weights(layout, qweight, scales, qzeros)
     if not x.is_cuda or (bias is not None and not bias.is_cuda):
         raise B200AwqError("b200awq: tensors must live on a CUDA device (there is no CPU path)")
     x2 = _x2d(x, K)

@@ -444,6 +444,40 @@ def tp70b_leg(torch, dist, rank, world, dev, steps, layers=None):
             ar(h)
         return h
 
+    # the same step with every collective-free segment as ONE persistent kernel (decode program): per layer
+    # [RMSNorm -> qkv -> o] | all-reduce | [RMSNorm -> gate|up -> SiLU*mul -> down] | all-reduce = 4 launches, not 10
+    from autoawq_b200.program import DecodeProgram
+
+    progs, prog_err = [], None
+    try:
+        h_in = h0
+        for qkv, o, gu, down in ws:
+            pa = DecodeProgram()
+            pa.layernorm_forward_cuda(h_in, nw, xn, 1e-5)
+            q = pa.gemm_forward_cuda(xn, qkv.qweight, qkv.scales, qkv.qzeros, 8)
+            y = pa.gemm_forward_cuda(q[:, :q_local], o.qweight, o.scales, o.qzeros, 8)
+            pa.build()
+            pb = DecodeProgram()
+            pb.layernorm_forward_cuda(y, nw, xn, 1e-5)
+            g = pb.gemm_forward_cuda(xn, gu.qweight, gu.scales, gu.qzeros, 8)
+            pb.silu_and_mul(act, g)
+            d = pb.gemm_forward_cuda(act, down.qweight, down.scales, down.qzeros, 8)
+            pb.build()
+            progs.append((pa, y, pb, d))
+            h_in = d
+        if not all(pa.fused and pb.fused for pa, _, pb, _ in progs):
+            prog_err = "a segment did not fit the fused kernels"
+    except Exception as ex:  # noqa: BLE001
+        prog_err = f"{type(ex).__name__}: {str(ex)[:160]}"
+
+    def step_programs():
+        for pa, y, pb, d in progs:
+            pa.run()
+            oneshot(y)
+            pb.run()
+            oneshot(d)
+        return progs[-1][3]
+
     def ar_only(collective="nccl"):
         ar = dist.all_reduce if collective == "nccl" else oneshot
         for _ in range(2 * c["layers"]):
@@ -455,9 +489,12 @@ def tp70b_leg(torch, dist, rank, world, dev, steps, layers=None):
                        f"o {H // world}x{H} + all-reduce, gate|up {H}x{2 * I // world}, down {I // world}x{H} + all-reduce]",
            "weights_gb_per_gpu": round(alg * c["layers"] / 1e9, 2)}
     res = {}
-    for name, fn in (("step", lambda: step("oneshot")), ("step_nccl", lambda: step("nccl")),
-                     ("no_collective", lambda: step("none")), ("allreduce_only", lambda: ar_only("oneshot")),
-                     ("allreduce_only_nccl", lambda: ar_only("nccl"))):
+    variants = [("step", lambda: step("oneshot")), ("step_nccl", lambda: step("nccl")),
+                ("no_collective", lambda: step("none")), ("allreduce_only", lambda: ar_only("oneshot")),
+                ("allreduce_only_nccl", lambda: ar_only("nccl"))]
+    if prog_err is None:
+        variants.append(("step_programs", step_programs))
+    for name, fn in variants:
         try:
             g, _ = capture(torch, fn)
             f = g.replay
@@ -475,6 +512,19 @@ def tp70b_leg(torch, dist, rank, world, dev, steps, layers=None):
     y1, y2, y3 = step("oneshot").float().clone(), step("nccl").float().clone(), step("nccl").float().clone()
     torch.cuda.synchronize()
     t = res["step"][0]
+    out["per_op_launches"] = {"tok_s": round(1.0 / t, 2), "ms_per_step": round(t * 1e3, 4),
+                              "launches_per_step": 10 * c["layers"]}
+    if "step_programs" in res and res["step_programs"][0] < t:
+        t = res["step_programs"][0]
+        out["path"] = (f"decode programs: {2 * c['layers']} persistent kernels ({progs[0][0].kind} / {progs[0][2].kind}) + "
+                       f"{2 * c['layers']} one-shot all-reduces per token")
+    else:
+        out["path"] = "per-op launches + one-shot all-reduces"
+    if "step_programs" in res:
+        out["decode_programs"] = {"tok_s": round(1.0 / res["step_programs"][0], 2),
+                                  "ms_per_step": round(res["step_programs"][0] * 1e3, 4), "launches_per_step": 4 * c["layers"]}
+    elif prog_err:
+        out["decode_programs"] = {"unavailable": prog_err}
     out.update({"tok_s": round(1.0 / t, 2), "ms_per_step": round(t * 1e3, 4), "cuda_graph": res["step"][1],
                 "collective": f"one-shot all-reduce over NVLink peer memory (csrc/comm.cu), fp16 [1, {H}] (16 KB) x "
                               f"{2 * c['layers']} per token, one kernel each, inside the CUDA graph",
