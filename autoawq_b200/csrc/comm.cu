@@ -18,6 +18,8 @@
 //   inbox[e & 1]; it cannot start e + 2 before every peer has signalled e + 1, i.e. finished reading e.
 //   No memset, no host round trip, nothing to reset.  A spin gives up after 2 s (dead peer) and raises the comm's
 //   error flag instead of hanging the GPU.
+// The DEFAULT protocol is the LL variant further down (data words that carry their own validity: one hop, no fence);
+// the flag protocol described here is kept behind knob 17 for comparison.
 //
 // Messages larger than the buffer (prefill) stay on NCCL (autoawq_b200/comm.py decides).
 #include <cuda_fp16.h>
@@ -52,7 +54,8 @@ __host__ __device__ inline size_t comm_inbox_bytes(int world, int max_elems) {
   return (size_t)2 * world * max_elems * sizeof(__half);
 }
 __host__ __device__ inline size_t comm_bytes(int world, int max_elems) {
-  return comm_inbox_bytes(world, max_elems) + 2 * 128;   // flags[2][<= 32] u32
+  // flag protocol: inbox + flags[2][<= 32] u32; LL protocol: 2 x the inbox (every 4 data bytes travel with 4 epoch bytes)
+  return 2 * comm_inbox_bytes(world, max_elems) + 2 * 128;
 }
 
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
@@ -129,6 +132,72 @@ __global__ void __launch_bounds__(kCommThreads, 1)
   if (tid == 0) state[0] = (int)e;
 }
 
+// ---------------------------------------------------------------------------------------------- LL protocol
+// The flag protocol above pays for: push, CTA barrier, fence.sys, flag store, flag poll, CTA barrier, reduce - two
+// NVLink hops and two fences in sequence (8.1 us at N = 2, 11.6 us at N = 8).  Here every 8-byte word carries its own
+// validity (NCCL's LL idea): {two fp16 values, 32-bit call number}.  A rank stores such words straight into every
+// peer's slot and polls its own slots word by word until the call number matches: ONE hop, no barrier, no fence, no
+// flag.  8-byte aligned stores do not tear; 16-byte vectors (two words) are used on both sides.  Same parity
+// double-buffering and device-resident call counter as above; same rank-ordered fp32 sum.
+__device__ __forceinline__ void st_relaxed_sys_u4(void* p, const uint4& v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_relaxed_sys_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
+__global__ void __launch_bounds__(kCommThreads, 1)
+    ll_allreduce_kernel(CommPeers peers, int rank, int world, int max_elems, __half* __restrict__ y, int n,
+                        int* __restrict__ state) {
+  const int tid = threadIdx.x;
+  const uint32_t e = (uint32_t)state[0] + 1u;
+  const int par = (int)(e & 1u);
+  const int nv = n >> 2;                                      // vectors of 4 halves = two LL words = 16 bytes on the wire
+  const size_t slot_bytes = (size_t)max_elems * 4;            // 2 halves -> 8 bytes
+  const size_t inbox_off = (size_t)par * world * slot_bytes;
+  const uint2* src = reinterpret_cast<const uint2*>(y);
+  for (int v = tid; v < nv; v += kCommThreads) {
+    const uint2 d = src[v];
+    const uint4 w = make_uint4(d.x, e, d.y, e);
+    for (int p = 0; p < world; ++p)
+      st_relaxed_sys_u4(peers.base[p] + inbox_off + (size_t)rank * slot_bytes + (size_t)v * 16, w);
+  }
+  const uint8_t* mine = peers.base[rank] + inbox_off;
+  uint2* dst = reinterpret_cast<uint2*>(y);
+  unsigned long long t0 = 0;
+  bool dead = false;
+  for (int v = tid; v < nv; v += kCommThreads) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = 0; q < world; ++q) {
+      const uint8_t* a = mine + (size_t)q * slot_bytes + (size_t)v * 16;
+      uint4 w = ld_relaxed_sys_u4(a);
+      int spins = 0;
+      while (!dead && (w.y != e || w.w != e)) {
+        if ((++spins & 1023) == 0) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 2000000000ull) {   // 2 s: a peer is gone - do not hang the GPU
+            state[1] = 1;
+            dead = true;
+          }
+        }
+        w = ld_relaxed_sys_u4(a);
+      }
+      const float2 f0 = __half22float2(u32_as_h2(w.x)), f1 = __half22float2(u32_as_h2(w.z));
+      acc[0] += f0.x;
+      acc[1] += f0.y;
+      acc[2] += f1.x;
+      acc[3] += f1.y;
+    }
+    dst[v] = make_uint2(h2_as_u32(__floats2half2_rn(acc[0], acc[1])), h2_as_u32(__floats2half2_rn(acc[2], acc[3])));
+  }
+  __syncthreads();
+  if (tid == 0) state[0] = (int)e;
+}
+
 int comm_create(int rank, int world, int max_elems, Comm** out, cudaError_t* err) {
   *out = nullptr;
   *err = cudaSuccess;
@@ -181,8 +250,14 @@ cudaError_t comm_open(Comm* c, const void* handles) {
 }
 
 cudaError_t comm_all_reduce(Comm* c, void* y, int n, cudaStream_t st) {
-  oneshot_allreduce_kernel<<<1, kCommThreads, 0, st>>>(c->peers, c->rank, c->world, c->max_elems, static_cast<__half*>(y), n,
-                                                       c->d_state);
+  // knob 17 = 1: the flag protocol (kept for comparison); default: LL words (one hop, no fences).  The two protocols
+  // share the buffer and the call counter but not their data layout: do not switch between calls that are in flight.
+  if (knob(17) == 1)
+    oneshot_allreduce_kernel<<<1, kCommThreads, 0, st>>>(c->peers, c->rank, c->world, c->max_elems, static_cast<__half*>(y),
+                                                         n, c->d_state);
+  else
+    ll_allreduce_kernel<<<1, kCommThreads, 0, st>>>(c->peers, c->rank, c->world, c->max_elems, static_cast<__half*>(y), n,
+                                                    c->d_state);
   return cudaGetLastError();
 }
 
