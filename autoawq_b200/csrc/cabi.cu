@@ -52,7 +52,7 @@ static bool carve(void* ws, size_t bytes, int M, int N, Ws* out) {
   out->acc = nullptr;
   if (ws == nullptr) return false;
   const int rows = M < kMaxSplitM ? M : kMaxSplitM;
-  const size_t need = kTicketBytes + (size_t)rows * N * sizeof(float);
+  const size_t need = kTicketBytes + (size_t)rows * N * 8;   // one 64-bit packed word (or two floats) per element
   if (bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15) != 0) return false;
   out->tickets = reinterpret_cast<int*>(ws);
   out->acc = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kTicketBytes);
@@ -85,7 +85,7 @@ size_t b200awq_workspace_bytes(int M, int K, int N) {
   (void)K;
   if (M < 0 || N <= 0) return 0;
   const int rows = M < kMaxSplitM ? M : kMaxSplitM;
-  return kTicketBytes + (size_t)rows * N * sizeof(float);
+  return kTicketBytes + (size_t)rows * N * 8;
 }
 
 int b200awq_set_knob(int key, int value) {

@@ -340,7 +340,8 @@ __global__ void __launch_bounds__(kV3Threads, 1)
                    const __half* __restrict__ scales, const int32_t* __restrict__ qzeros,
                    const __half* __restrict__ bias, __half* __restrict__ y, float* __restrict__ acc_ws,
                    int* __restrict__ tickets, int M, int K, int N, int G, int g_shift,
-                   const uint8_t* __restrict__ next_w, long long next_bytes, int dbg, int l2_ahead, const V3Moe moe) {
+                   const uint8_t* __restrict__ next_w, long long next_bytes, int dbg, int l2_ahead, const V3Moe moe,
+                   int packed) {
   constexpr int NS = V3Smem<MT, SPW>::kStages;
   __shared__ int s_slot[8];       // MOE: output row of each of the job's slots (-1 = padding)
   int row_off = 0;                // MOE: first row of the job's expert in the stacked tensor
@@ -533,7 +534,11 @@ __global__ void __launch_bounds__(kV3Threads, 1)
       if (cur_cb >= 0 && ntl > 0) {
         // this warp's run crosses a column block: push its pending sums alone (rare)
         v3_dump_cols<MT>(my_red, ycol, lane);
-        v3_push_warp<MT>(my_red, cur_cb, ntl, TPC, lane, bias, y, acc_ws, tickets, M, N, scat);
+        if (packed)
+          v3_atom_cols<MT, 32>(my_red, 1, 0, cur_cb, ntl, TPC, lane, bias, y, reinterpret_cast<unsigned long long*>(acc_ws),
+                               M, N, scat);
+        else
+          v3_push_warp<MT>(my_red, cur_cb, ntl, TPC, lane, bias, y, acc_ws, tickets, M, N, scat);
       }
       cur_cb = cb;
       ntl = 0;
@@ -573,6 +578,22 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   }
   named_bar_sync_gv(1, kV3Warps * 32);
   if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 4] = gtimer();
+  if (packed) {
+    // packed epilogue: one returning atomic per (token, column) and column-block group; whoever completes a column
+    // finalises it on the spot - no ticket pass, no read-back pass (gemv_tile.cuh)
+    int w0 = 0;
+    while (w0 < kV3Warps) {
+      const int cbg = warp_cb[w0];
+      int w1 = w0 + 1, tiles = warp_ntl[w0];
+      while (w1 < kV3Warps && warp_cb[w1] == cbg) tiles += warp_ntl[w1++];
+      if (cbg >= 0)
+        v3_atom_cols<MT, kV3Warps * 32>(red + (size_t)w0 * MT * kGvRedStride, w1 - w0, MT * kGvRedStride, cbg, tiles, TPC,
+                                        ct, bias, y, reinterpret_cast<unsigned long long*>(acc_ws), M, N, scat);
+      w0 = w1;
+    }
+    if (dbg && ct == 0 && blockIdx.x < 256) g_v3_dbg[blockIdx.x * 8 + 7] = gtimer();
+    return;
+  }
   // pass 1: all column-block groups of this CTA (consecutive warps with the same block) -> workspace
   {
     int w0 = 0;
@@ -682,7 +703,7 @@ static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cud
                        reinterpret_cast<const __half*>(a.scales), a.qzeros, reinterpret_cast<const __half*>(a.bias),
                        reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M, a.K, a.N, a.G, g_shift,
                        reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3) == 1 ? 1 : 0, knob(8) > 0 ? knob(8) - 1 : 0,
-                       V3Moe{});
+                       V3Moe{}, (a.K / kV3TileRows < 256 && knob(18) == 0) ? 1 : 0);   // knob 18 = 1: ticket epilogue
 }
 
 // Grouped launch: grid.y = sorted_len / 8 jobs (most of them padding: they exit at once).  Needs hbs * 8 rows of fp32
@@ -712,7 +733,7 @@ cudaError_t gemv_v3_moe(const void* x, int x_per_slot, const int32_t* qweight, c
     return launch_kernel(kern, dim3(grid, hbs), dim3(kV3Threads), smem, st, tm, reinterpret_cast<const __half*>(x),
                          (int64_t)K, reinterpret_cast<const __half*>(scales), qzeros, static_cast<const __half*>(nullptr),
                          reinterpret_cast<__half*>(y), acc_ws, tickets, mt, K, N, G, g_shift,
-                         static_cast<const uint8_t*>(nullptr), 0LL, 0, 0, moe);
+                         static_cast<const uint8_t*>(nullptr), 0LL, 0, 0, moe, 0);   // (grouped jobs keep the ticket epilogue)
   };
   if (tokens <= 1) return go(gemv_v3_kernel<1, 3, false, true>, V3Smem<1, 3>::bytes, 1);
   if (tokens <= 2) return go(gemv_v3_kernel<2, 2, false, true>, V3Smem<2, 2>::bytes, 2);

@@ -101,6 +101,65 @@ __device__ __forceinline__ void v3_finalize(int cb, int t, const __half* __restr
   }
   if (t == 0) tickets[cb] = 0;
 }
+// ---------------------------------------------------------------------------------- packed split-K epilogue
+// One 64-bit word per (token, column) carries the partial sums AND how many tiles have contributed (the decode
+// program's hand-off word, csrc/program.cu):  word = tiles << 48 | sum of (round(v * 2^24) + tiles * 2^39).
+// Every contributor does ONE atom.add.u64 WITH RETURN: the one whose add completes the tile count holds the complete
+// sum (old + own), rounds it to fp16 (+ bias), stores y and writes the zero back.  One L2 round trip instead of three
+// (REDs -> ticket -> read back), no tickets, and - integer addition is associative - the result no longer depends on
+// the order in which CTAs arrive: the per-op GEMV is bit-reproducible.  Needs K / 64 < 256 tiles per column and
+// |partial| < tiles * 32768 (fp16 outputs beyond that are inf anyway); resolution 2^-24 = one fp16 subnormal step.
+constexpr float kV3FixScale = 16777216.0f;
+__device__ __forceinline__ unsigned long long v3_pack(float v, int ntl) {
+  long long f = __float2ll_rn(v * kV3FixScale);
+  const long long lim = ((long long)ntl << 39) - 1;
+  f = f > lim ? lim : (f < -lim ? -lim : f);
+  return ((unsigned long long)ntl << 48) + (unsigned long long)(((long long)ntl << 39) + f);
+}
+__device__ __forceinline__ unsigned long long atom_add_u64(unsigned long long* p, unsigned long long v) {
+  unsigned long long old;
+  asm volatile("atom.relaxed.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+  return old;
+}
+template <int MT, int NT>
+__device__ __forceinline__ void v3_atom_cols(float* cols, int nsrc, int src_stride, int cb, int ntl, int TPC, int t,
+                                             const __half* __restrict__ bias, __half* __restrict__ y,
+                                             unsigned long long* __restrict__ ws64, int M, int N,
+                                             V3Scatter sc = V3Scatter()) {
+  const int n_base = cb * kV3TileCols;
+  const long long off = (long long)TPC << 39;
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+    if (m < M && (sc.ids == nullptr || sc.ids[m] >= 0)) {
+      int row = m;
+      float mulw = 1.f;
+      if (sc.ids != nullptr) {
+        row = sc.ids[m];
+        if (sc.tw != nullptr) mulw = sc.tw[row];
+      }
+      for (int c = t; c < kV3TileCols; c += NT) {
+        float v = 0.f;
+        for (int sidx = 0; sidx < nsrc; ++sidx) {
+          v += cols[sidx * src_stride + m * kV3TileCols + c];
+          cols[sidx * src_stride + m * kV3TileCols + c] = 0.f;
+        }
+        const int n = n_base + c;
+        unsigned long long* p = ws64 + (int64_t)m * N + n;
+        const unsigned long long mine = v3_pack(v, ntl);
+        const unsigned long long old = atom_add_u64(p, mine);
+        if ((int)(old >> 48) + ntl == TPC) {           // this add completed the column: finalise it
+          const unsigned long long tot = old + mine;
+          float r = __ll2float_rn((long long)(tot & 0xFFFFFFFFFFFFull) - off) * (1.0f / kV3FixScale);
+          *p = 0ull;                                     // (the next launch touches the workspace after its PDL wait)
+          if (bias != nullptr) r += __half2float(bias[n]);
+          if (sc.ids != nullptr) r *= mulw;
+          y[(int64_t)row * N + n] = __float2half_rn(r);
+        }
+      }
+    }
+  }
+}
+
 // Warp-level push (a warp's run crossed a column block; rare).
 template <int MT>
 __device__ __forceinline__ bool v3_push_warp(float* cols, int cb, int ntl, int TPC, int lane,

@@ -52,7 +52,8 @@ const char* b200awq_error_string(int code);
 /* last CUDA error text seen by this library on the calling thread ("" if none) */
 const char* b200awq_last_cuda_error(void);
 
-/* Bytes of scratch the forward entry points may need for (M, K, N) (split-K partials + tickets).
+/* Bytes of scratch the forward entry points may need for (M, K, N): 16 KB of tickets + min(M, 64) * N 64-bit words
+ * (split-K partials: packed fixed-point sum + tile count per element for the M <= 8 GEMV, fp32 pairs otherwise).
  * The caller allocates once (zero-initialised!) and passes it to every call; the library restores the
  * all-zero ticket state before each kernel exits, so one buffer serves any number of calls on one stream. */
 size_t b200awq_workspace_bytes(int M, int K, int N);
@@ -143,6 +144,8 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *   key 12: 2 = grouped_gemm_forward always uses the register-staged grouped kernel
  *   key 13: decode program (read at b200awq_program_create): minimum tiles per participating CTA; ops with fewer
  *           tiles per CTA are shared by fewer CTAs (0 = every CTA takes part in every op, the default: measured best)
+ *   key 18: 1 = the persistent GEMV (M <= 8) uses round 1's split-K epilogue (fp32 REDs, tickets, read-back) instead of
+ *           the packed one (one returning 64-bit atomic per element; bit-reproducible)
  *   key 17: 1 = b200awq_comm_all_reduce uses the flag protocol (push, fence, flag, wait, reduce) instead of the default
  *           LL protocol (8-byte words carrying {2 x fp16, call number}: one NVLink hop, no fences)
  *   key 16: decode-program watchdog in seconds (0 = the default 0.5 s): every spin of the program kernels gives up
