@@ -703,7 +703,11 @@ static cudaError_t launch_v3(const GemmArgs& a, float* acc_ws, int* tickets, cud
                        reinterpret_cast<const __half*>(a.scales), a.qzeros, reinterpret_cast<const __half*>(a.bias),
                        reinterpret_cast<__half*>(a.y), acc_ws, tickets, a.M, a.K, a.N, a.G, g_shift,
                        reinterpret_cast<const uint8_t*>(nx.ptr), nx.bytes, knob(3) == 1 ? 1 : 0, knob(8) > 0 ? knob(8) - 1 : 0,
-                       V3Moe{}, (a.K / kV3TileRows < 256 && knob(18) == 0) ? 1 : 0);   // knob 18 = 1: ticket epilogue
+                       // packed epilogue at M = 1 only: there it saves the ticket and read-back round trips (4096 x 4096:
+                       // 8.75 -> 7.18 us); for M >= 2 the returning 64-bit atomics cost more than they save on the
+                       // larger shapes (4096 x 14336, M = 8: 32 -> 49 us), so those keep fp32 REDs + tickets.
+                       // knob 18 = 1: ticket epilogue everywhere
+                       V3Moe{}, (MT == 1 && a.K / kV3TileRows < 256 && knob(18) == 0) ? 1 : 0);
 }
 
 // Grouped launch: grid.y = sorted_len / 8 jobs (most of them padding: they exit at once).  Needs hbs * 8 rows of fp32

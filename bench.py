@@ -766,9 +766,10 @@ def main():
         per_op["linear_frac"] = round(lin_ach / peaks["hbm_gbs"], 4)
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(ach / peaks["hbm_gbs"], 4),
-                # dram__bytes_read + write per program_kernel launch: profiles/r01_ncu_program_kernel_bench.csv
-                # (3,629.7 MB read + 27-29 MB written; algorithmic 3,626 MB)
-                "traffic": 3658000000 if a.layers == LAYERS else None,
+                # dram__bytes_read + write per program_kernel launch, one ncu --set full capture of this command:
+                # profiles/r02_ncu_program_kernel.md (3,629.7 MB read + 30.5 MB written; algorithmic 3,626 MB).
+                # Captured for the split-K kernel; the stream kernel reads the same bytes by construction (no ncu).
+                "traffic": (3629674000 + 30530560) if (a.layers == LAYERS and prog.kind != "stream") else None,
                 "kernel": ("stream_program_kernel" if prog.kind == "stream" else "program_kernel") +
                           " (persistent decode program: 128 linears + glue per launch)",
                 "peak_src": peaks["src"] + " (hbm_gbs)",

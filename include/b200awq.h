@@ -144,8 +144,8 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *   key 12: 2 = grouped_gemm_forward always uses the register-staged grouped kernel
  *   key 13: decode program (read at b200awq_program_create): minimum tiles per participating CTA; ops with fewer
  *           tiles per CTA are shared by fewer CTAs (0 = every CTA takes part in every op, the default: measured best)
- *   key 18: 1 = the persistent GEMV (M <= 8) uses round 1's split-K epilogue (fp32 REDs, tickets, read-back) instead of
- *           the packed one (one returning 64-bit atomic per element; bit-reproducible)
+ *   key 18: 1 = the persistent GEMV uses round 1's split-K epilogue (fp32 REDs, tickets, read-back) also at M = 1,
+ *           instead of the packed one (one returning 64-bit atomic per element; bit-reproducible)
  *   key 17: 1 = b200awq_comm_all_reduce uses the flag protocol (push, fence, flag, wait, reduce) instead of the default
  *           LL protocol (8-byte words carrying {2 x fp16, call number}: one NVLink hop, no fences)
  *   key 16: decode-program watchdog in seconds (0 = the default 0.5 s): every spin of the program kernels gives up
