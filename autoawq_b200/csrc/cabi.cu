@@ -100,6 +100,7 @@ int b200awq_debug_read(void* host_dst, size_t bytes) {
   if (knob(3) == 2) return fold(program_debug_read(host_dst, bytes));
   if (knob(3) == 3) return fold(program_abort_read(host_dst, bytes));
   if (knob(3) == 8) return fold(stream_debug_read(host_dst, bytes));
+  if (knob(3) == 9) return fold(gemm_tcq_debug_read(host_dst, bytes));
   return fold(gemv_v3_debug_read(host_dst, bytes));
 }
 

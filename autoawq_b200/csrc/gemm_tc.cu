@@ -44,6 +44,7 @@ struct TcParams {
   int n_tiles, m_tiles, ksplit;
   int has_tmq;     // GEMM layout: a tensor map over qweight is available for L2 prefetch
   int g_shift;     // log2(G) when G is a power of two, else 31 (G == K: one group) - no integer division on device
+  int dbg;         // small-M kernel: record phase timestamps (knob 3 == 9)
 };
 
 template <int BT>
@@ -287,7 +288,9 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
 
   if (warp == 0) {
     // ================================================================= TMA producer (X tiles)
-    if (lane == 0) {
+    // The whole warp walks the loop and one elected lane issues (see the MMA warp below for why).
+    {
+      const bool leader = elect_one();
       // GEMM layout: pull the packed weights of the next kL2Ahead k-steps from HBM into L2 (TMA prefetch, no
       // smem destination) so that the producers' register prefetch only has to cover L2 latency.  Weights
       // do not depend on the predecessor kernel: this starts before the PDL wait.
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
       };
       auto pf_step = [&]() {
         const int nt = wp / (p.ksplit * p.m_tiles);
-        tma_prefetch_l2_2d(&tmq, nt * 16, sp * kBK);
+        if (leader) tma_prefetch_l2_2d(&tmq, nt * 16, sp * kBK);
         if (++sp == sp_end) {
           wp += gridDim.x;
           if (wp < n_work) pf_range(); else pf_valid = false;
@@ -318,8 +321,11 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
         const int s_begin = (int)((int64_t)KS * ks / p.ksplit), s_end = (int)((int64_t)KS * (ks + 1) / p.ksplit);
         for (int s = s_begin; s < s_end; ++s) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::kXStageBytes);
-          tma_load_2d(x_base + (size_t)stage * Cfg::kXStageBytes, &tmx, &full[stage], s * kBK, mt * BT);
+          if (leader) {
+            mbar_arrive_expect_tx(&full[stage], Cfg::kXStageBytes);
+            tma_load_2d(x_base + (size_t)stage * Cfg::kXStageBytes, &tmx, &full[stage], s * kBK, mt * BT);
+          }
+          __syncwarp();
           if (++stage == NS) { stage = 0; phase ^= 1; }
           if (pf_valid) pf_step();
         }
@@ -327,8 +333,20 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
-    if (lane == 0) {
+    // The WHOLE warp walks the loop (waits, stage bookkeeping, descriptors) and one elected lane issues, so that every
+    // operand of the tcgen05 instructions is warp-uniform for the compiler (uniform registers).  Under `if (lane == 0)`
+    // the same operands are divergent values and each UTCHMMA / UTCBAR came wrapped in an ELECT + 5 x R2UR + retry loop:
+    // ~130 instructions and ~700 clk per k-step on ONE thread, more than the 512 clk the four 128x256x16 MMAs of a
+    // k-step take (r2 ncu: tensor pipe 57 % active at M = 4096) - the issue loop, not the tensor pipe, set the pace.
+    {
       constexpr uint32_t idesc = umma_idesc_f16(kTileN, BT, (LAYOUT == 0 || LAYOUT == 3) ? 1 : 0, 0);
+      constexpr bool kMnMajorA = (LAYOUT == 0 || LAYOUT == 3);
+      const bool leader = elect_one();
+      // MN-major, SW128: LBO = stride between 64-n atoms (8192), SBO = stride between 8-k atoms (1024); K-major SW128
+      // otherwise.  Descriptors advance by adding (byte offset >> 4) to the start-address field (smem < 256 KB: no carry).
+      const uint64_t da0 = kMnMajorA ? umma_smem_desc(smem_u32(a_base), 8192, 1024) : umma_smem_desc(smem_u32(a_base), 16, 1024);
+      const uint64_t db0 = umma_smem_desc(smem_u32(x_base), 16, 1024);
+      constexpr uint32_t kAStep = kMnMajorA ? (2048u >> 4) : (32u >> 4);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -343,24 +361,20 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
         for (int s = s_begin; s < s_end; ++s) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_base + (size_t)stage * kAStageBytes);
-          const uint32_t x_addr = smem_u32(x_base + (size_t)stage * Cfg::kXStageBytes);
+          const uint64_t da = da0 + (uint64_t)((uint32_t)(stage * kAStageBytes) >> 4);
+          const uint64_t db = db0 + (uint64_t)((uint32_t)(stage * Cfg::kXStageBytes) >> 4);
+          if (leader) {
 #pragma unroll
-          for (int k16 = 0; k16 < kBK / 16; ++k16) {
-            uint64_t da, db;
-            if (LAYOUT == 0 || LAYOUT == 3) {
-              // MN-major, SW128: LBO = stride between 64-n atoms (8192), SBO = stride between 8-k atoms (1024)
-              da = umma_smem_desc(a_addr + k16 * 2048, 8192, 1024);
-            } else {
-              da = umma_smem_desc(a_addr + k16 * 32, 16, 1024);  // K-major SW128
-            }
-            db = umma_smem_desc(x_addr + k16 * 32, 16, 1024);    // K-major SW128
-            umma_f16_ss(d_tmem, da, db, idesc, (s > s_begin || k16 > 0) ? 1u : 0u);
+            for (int k16 = 0; k16 < kBK / 16; ++k16)
+              umma_f16_ss(d_tmem, da + (uint64_t)(k16 * kAStep), db + (uint64_t)(k16 * (32 >> 4)), idesc,
+                          (s > s_begin || k16 > 0) ? 1u : 0u);
+            umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above retire
           }
-          umma_commit(&empty[stage]);  // frees this smem stage when the MMAs above retire
+          __syncwarp();
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[buf]);  // accumulator complete
+        if (leader) umma_commit(&tmem_full[buf]);  // accumulator complete
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
@@ -495,6 +509,388 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
   }
 }
 
+// ------------------------------------------------------------ small-M kernel (TMA-staged packed weights)
+// M <= 128 on the GEMM layout is HBM-bound; the kernel above is latency-bound there (its producers pull the packed
+// words L2 -> registers through a 6-deep ring: ~500-900 clk per k-step whatever the token count, r2 M sweep).  This
+// variant keeps the MMA / descriptor / epilogue machinery and changes the three things that bound it:
+//   * the packed weights of a k-step (4 KB tile + the group's 256 B of scales + 64 B of zeros) arrive by TMA in a
+//     deep shared-memory ring (kNQ = 20..28 stages ~ 100 KB in flight per SM, independent of registers), issued by a
+//     dedicated warp that never waits for activations (weights do not depend on the predecessor kernel);
+//   * the producers read a stage with conflict-free LDS, dequantise exactly as before (bit-identical A tile) and run
+//     one k-step ahead of their own stores;
+//   * work is cut into CONTIGUOUS RANGES of the linearised (n-tile, k-step) sequence, one range per SM: every SM
+//     streams the same number of bytes whatever N / 128 is (the (tile, k-split) items of the kernel above leave
+//     224 tiles on 148 SMs two waves deep).  A range crosses at most a few n-tiles = segments; a segment that holds a
+//     whole K column stores fp16 directly, a partial one adds fp32 into the caller's zeroed workspace and bumps the
+//     tile's ticket by its number of k-steps; the contributor that completes K rounds, adds the bias, restores zeros.
+template <int BT>
+struct TcqCfg {
+  static constexpr int kNS = BT <= 32 ? 6 : 4;                             // A stages (producers -> MMA); even
+  static constexpr int kNX = BT <= 16 ? 16 : (BT <= 64 ? 8 : 5);  // X stages (TMA -> MMA), own ring
+  static constexpr int kNQ = BT <= 64 ? 20 : 16;                           // packed-weight stages (TMA -> producers); even
+  static constexpr int kXStageBytes = BT * kBK * 2;
+  static constexpr int kQTileBytes = 16 * 4 * kBK;                         // 64 rows x 16 words
+  static constexpr int kQTxBytes = kQTileBytes + 256 + 64;                 // + scales of 128 columns + zeros of 16 words
+  static constexpr int kQStageBytes = 4480;                                // padded to a multiple of 128
+  static constexpr int kAccCols = BT < 32 ? 32 : BT;
+  // Independent accumulators per buffer: the k16 slices of a k-step go to accumulator k16 % kNAcc and the epilogue adds
+  // them.  A 128 x BT x 16 MMA with BT <= 128 retires in a few clocks of tensor-pipe time but ~130 clk after issue, and
+  // MMAs into ONE accumulator serialise on that latency (4 x 130 clk per k-step = the measured 275 ns of the third
+  // version, whatever BT); separate accumulators pipeline.
+  static constexpr int kNAcc = BT <= 64 ? 4 : 2;
+  static constexpr int kTmemCols = 2 * kNAcc * kAccCols;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation: power of two <= 512");
+  static constexpr int kTeams = 2;       // producer teams of 8 warps: team t dequantises k-steps t, t + 2, ...
+  static constexpr int kQWarps = 2;      // Q-TMA warps: warp w issues the bulk copies of k-steps w, w + 2, ... (3 would cap registers at 72: spills)
+  static constexpr int kThreads = 192 + 256 * kTeams + 32 * kQWarps;   // X-TMA, MMA, 4 epilogue, 16 producer warps, 2 Q-TMA
+  static constexpr size_t kSmemBytes = (size_t)kNS * kAStageBytes + (size_t)kNX * kXStageBytes +
+                                       (size_t)kNQ * kQStageBytes + 1024 /*align slack*/ + 1024 /*barriers*/;
+  static_assert(kNS >= kTeams && kNQ >= kTeams && kNQ >= kQWarps, "a ring index wraps at most once per advance");
+  static_assert(kSmemBytes <= 232448, "shared memory per CTA");
+};
+
+__device__ __forceinline__ uint32_t lds_u1(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
+// Phase timestamps (globaltimer, ns) of the last small-M launch, 8 per CTA, written only when knob 3 == 9 (TcParams::dbg):
+// [0] entry, [1] setup done (barriers, TMEM), [2] first packed stage landed, [3] producers done, [4] MMA issuer done,
+// [5] last accumulator drained, [6] epilogue done (incl. finalisation), [7] number of segments.
+__device__ unsigned long long g_tcq_dbg[256 * 8];
+__device__ __forceinline__ unsigned long long tcq_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+cudaError_t gemm_tcq_debug_read(void* dst, size_t bytes) {
+  return cudaMemcpyFromSymbol(dst, g_tcq_dbg, bytes < sizeof(g_tcq_dbg) ? bytes : sizeof(g_tcq_dbg));
+}
+
+template <int BT>
+__global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
+    gemm_tcq_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq, const TcParams p) {
+  using Cfg = TcqCfg<BT>;
+  constexpr int NS = Cfg::kNS, NX = Cfg::kNX, NQ = Cfg::kNQ;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_base = smem;                                              // NS x 16 KB
+  uint8_t* x_base = a_base + (size_t)NS * kAStageBytes;                // NX x BT*128 B
+  uint8_t* q_base = x_base + (size_t)NX * Cfg::kXStageBytes;           // NQ x 4480 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(q_base + (size_t)NQ * Cfg::kQStageBytes);
+  uint64_t* full = bars;                     // [NS]  8 producer warps (one team)
+  uint64_t* empty = full + NS;               // [NS]  tcgen05.commit
+  uint64_t* xfull = empty + NS;              // [NX]  expect_tx of the activation tile
+  uint64_t* xempty = xfull + NX;             // [NX]  tcgen05.commit
+  uint64_t* qfull = xempty + NX;             // [NQ]  expect_tx of the packed stage
+  uint64_t* qempty = qfull + NQ;             // [NQ]  8 producer warps (one team)
+  uint64_t* tmem_full = qempty + NQ;         // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  int* s_flag = reinterpret_cast<int*>(tmem_empty + 3);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  const bool dbg = (p.dbg & 1) != 0 && blockIdx.x < 256;
+  unsigned long long* dbg_row = g_tcq_dbg + blockIdx.x * 8;
+  if (dbg && threadIdx.x == 0) dbg_row[0] = tcq_timer();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmx);
+    tma_prefetch_desc(&tmq);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 8);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < NX; ++s) {
+      mbar_init(&xfull[s], 1);
+      mbar_init(&xempty[s], 1);
+    }
+    for (int s = 0; s < NQ; ++s) {
+      mbar_init(&qfull[s], 1);
+      mbar_init(&qempty[s], 8);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg_row[1] = tcq_timer();
+
+  // this CTA's contiguous range of the linearised (n-tile, k-step) sequence
+  const int KS = p.K / kBK;
+  const long long T = (long long)p.n_tiles * KS;
+  const int t_begin = (int)(T * (long long)blockIdx.x / (long long)gridDim.x);
+  const int t_end = (int)(T * (long long)(blockIdx.x + 1) / (long long)gridDim.x);
+  constexpr int kQWarp = 6 + 8 * Cfg::kTeams;
+
+  if (warp >= kQWarp) {
+    // ================================================================= Q-TMA: packed weights + group constants
+    // kQWarps warps, warp w owns k-steps w, w + kQWarps, ... of the CTA's range: ONE warp issuing the three bulk copies of
+    // every step (wait, expect_tx, tensor tile, scales, zeros: ~500 clk of dependent uniform-datapath work) was the
+    // k-step time of the second version - its ring was never full while the producers waited for data (ncu source page).
+    // The whole warp walks the loop, one elected lane issues: uniform operands, no per-instruction retry loops.
+    {
+      const bool leader = elect_one();
+      const int qw = warp - kQWarp;
+      const uint32_t NW = (uint32_t)p.N >> 3;
+      const int nsteps = t_end - t_begin;
+      int nt = (t_begin + qw) / KS, sk = (t_begin + qw) - nt * KS;
+      int qs = qw;            // kQWarps <= NQ
+      uint32_t qph = 0;
+      for (int i = qw; i < nsteps; i += Cfg::kQWarps) {
+        mbar_wait(&qempty[qs], qph ^ 1);
+        uint8_t* dst = q_base + (size_t)qs * Cfg::kQStageBytes;
+        const uint32_t g = (uint32_t)(sk * kBK) >> p.g_shift;
+        if (leader) {
+          mbar_arrive_expect_tx(&qfull[qs], Cfg::kQTxBytes);
+          tma_load_2d(dst, &tmq, &qfull[qs], nt * 16, sk * kBK);
+          bulk_load_1d(dst + Cfg::kQTileBytes, p.scales + (size_t)g * p.N + (size_t)nt * kTileN, 256, &qfull[qs]);
+          bulk_load_1d(dst + Cfg::kQTileBytes + 256, p.qzeros + (size_t)g * NW + (size_t)nt * 16, 64, &qfull[qs]);
+        }
+        __syncwarp();
+        qs += Cfg::kQWarps;
+        if (qs >= NQ) { qs -= NQ; qph ^= 1; }
+        sk += Cfg::kQWarps;
+        while (sk >= KS) { sk -= KS; ++nt; }
+      }
+    }
+  } else if (warp == 0) {
+    // ================================================================= X-TMA: activation tiles, own ring (the tiles
+    // come from L2 with ~1 us of latency: tying them to the NS A stages made that latency the k-step time)
+    {
+      const bool leader = elect_one();
+      pdl_wait();  // the activations are the predecessor's output
+      int xs = 0;
+      uint32_t xph = 0;
+      for (int t = t_begin; t < t_end;) {
+        const int nt = t / KS, s0 = t - nt * KS;
+        const int s1 = (KS - s0 < t_end - t) ? KS : s0 + (t_end - t);
+        for (int s = s0; s < s1; ++s) {
+          mbar_wait(&xempty[xs], xph ^ 1);
+          if (leader) {
+            mbar_arrive_expect_tx(&xfull[xs], Cfg::kXStageBytes);
+            tma_load_2d(x_base + (size_t)xs * Cfg::kXStageBytes, &tmx, &xfull[xs], s * kBK, 0);
+          }
+          __syncwarp();
+          if (++xs == NX) { xs = 0; xph ^= 1; }
+        }
+        t += s1 - s0;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    // The WHOLE warp walks the loop (waits, stage bookkeeping, descriptors) and one elected lane issues: everything the
+    // tcgen05 instructions consume is then warp-uniform for the compiler (uniform registers).  Under `if (lane == 0)`
+    // the same operands are divergent values, and every UTCHMMA / UTCBAR came wrapped in an ELECT + 5 x R2UR + retry
+    // loop: ~130 instructions and ~700 clk per k-step on ONE thread - the k-step time of the first version (ncu source
+    // page: the producers' top stall was the wait for the MMA's stage release).
+    {
+      constexpr uint32_t idesc = umma_idesc_f16(kTileN, BT, 1, 0);
+      const bool leader = elect_one();
+      const int mma_per_step = (p.dbg & 8) ? 0 : ((p.dbg & 16) ? 1 : kBK / 16);
+      const uint32_t a_base_s = smem_u32(a_base), x_base_s = smem_u32(x_base);
+      const uint64_t da0 = umma_smem_desc(a_base_s, 8192, 1024);   // MN-major SW128; start address in bits [0, 14)
+      const uint64_t db0 = umma_smem_desc(x_base_s, 16, 1024);     // K-major SW128
+      int stage = 0, xs = 0;
+      uint32_t phase = 0, xph = 0;
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++it) {
+        const int nt = t / KS, s0 = t - nt * KS;
+        const int s1 = (KS - s0 < t_end - t) ? KS : s0 + (t_end - t);
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tmem_empty[buf], use ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * Cfg::kNAcc * Cfg::kAccCols);
+        for (int s = s0; s < s1; ++s) {
+          mbar_wait(&xfull[xs], xph);
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          // descriptors advance by adding (byte offset >> 4) to the start-address field (no carry: smem < 256 KB)
+          const uint64_t da = da0 + (uint64_t)((uint32_t)(stage * kAStageBytes) >> 4);
+          const uint64_t db = db0 + (uint64_t)((uint32_t)(xs * Cfg::kXStageBytes) >> 4);
+          if (leader) {
+#pragma unroll
+            for (int k16 = 0; k16 < kBK / 16; ++k16)
+              if (k16 < mma_per_step)   // (4 unless a timing experiment is on: knob 20)
+                umma_f16_ss(d_tmem + (uint32_t)((k16 % Cfg::kNAcc) * Cfg::kAccCols), da + (uint64_t)(k16 * (2048 >> 4)),
+                            db + (uint64_t)(k16 * (32 >> 4)), idesc, (s > s0 || k16 >= Cfg::kNAcc) ? 1u : 0u);
+            umma_commit(&empty[stage]);
+            umma_commit(&xempty[xs]);
+          }
+          __syncwarp();
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+          if (++xs == NX) { xs = 0; xph ^= 1; }
+        }
+        if (leader) umma_commit(&tmem_full[buf]);
+        __syncwarp();
+        t += s1 - s0;
+      }
+      if (dbg && leader) { dbg_row[4] = tcq_timer(); dbg_row[7] = (unsigned long long)it; }
+    }
+  } else if (warp < 6) {
+    // ================================================================= epilogue (4 warps)
+    const int et = threadIdx.x - 64;  // 0..127
+    const int q4 = warp & 3;          // TMEM lane quadrant this warp may read
+    pdl_wait();                       // outputs / workspace may alias memory the predecessor still uses
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++it) {
+      const int nt = t / KS, s0 = t - nt * KS;
+      const int s1 = (KS - s0 < t_end - t) ? KS : s0 + (t_end - t);
+      const bool whole = (s0 == 0 && s1 == KS);
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tmem_full[buf], use);
+      tc_fence_after();
+      const int n = nt * kTileN + q4 * 32 + lane;   // N % 128 == 0: always in range
+      const float bias_v = p.bias != nullptr ? __half2float(p.bias[n]) : 0.f;
+      const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * Cfg::kNAcc * Cfg::kAccCols);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BT; c0 += 16) {
+        // the kNAcc partial accumulators of 16 tokens, added in a fixed order
+        uint32_t v[16], w[16];
+        float f[16];
+        tmem_ld_32x16(tbuf + (uint32_t)c0, v);
+        tmem_ld_32x16(tbuf + (uint32_t)(Cfg::kAccCols + c0), w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+        if constexpr (Cfg::kNAcc == 4) {
+          tmem_ld_32x16(tbuf + (uint32_t)(2 * Cfg::kAccCols + c0), v);
+          tmem_ld_32x16(tbuf + (uint32_t)(3 * Cfg::kAccCols + c0), w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
+        }
+        if (c0 < p.M) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = c0 + j;
+            if (m < p.M) {
+              if (whole)
+                p.y[(int64_t)m * p.N + n] = __float2half_rn(f[j] + bias_v);
+              else
+                red_add_f32(&p.acc_ws[(int64_t)m * p.N + n], f[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[buf]);
+      if (dbg && et == 0) dbg_row[5] = tcq_timer();
+      if (!whole) {
+        // relaxed REDs -> CTA-scope barrier -> one acq_rel ticket (release is cumulative over what the barrier ordered)
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          const int prev = atom_add_acq_rel(&p.tickets[nt], s1 - s0);
+          *s_flag = (prev + (s1 - s0) == KS);
+        }
+        named_bar_sync(1, 128);
+        const bool last = *s_flag != 0;
+        named_bar_sync(1, 128);  // everyone has read the flag before a later segment rewrites it
+        if (last) {
+          // all loads of a batch of 16 tokens are in flight before the first store (one L2 round trip per batch, not
+          // one per token: the first version spent 0.45 us per token here)
+          for (int m0 = 0; m0 < p.M; m0 += 16) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              f[j] = (m0 + j < p.M) ? ld_relaxed_f32(&p.acc_ws[(int64_t)(m0 + j) * p.N + n]) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (m0 + j < p.M) {
+                p.acc_ws[(int64_t)(m0 + j) * p.N + n] = 0.f;
+                p.y[(int64_t)(m0 + j) * p.N + n] = __float2half_rn(f[j] + bias_v);
+              }
+            }
+          }
+          if (et == 0) p.tickets[nt] = 0;
+        }
+      }
+      t += s1 - s0;
+    }
+    if (dbg && et == 0) dbg_row[6] = tcq_timer();
+  } else {
+    // ================================================================= dequant producers (2 teams x 8 warps)
+    // Team t owns k-steps t, t + 2, ... of the CTA's range (A stage i % NS, packed stage i % NQ): the two teams'
+    // [wait, LDS, dequant, STS, proxy fence, arrive] chains overlap, so the chain's latency is paid once per two steps.
+    const int pt = threadIdx.x - 192;
+    const int team = pt >> 8;
+    const int dt = pt & 255;  // 0..255 within the team
+    const uint32_t a_base_s = smem_u32(a_base);
+    const uint32_t q_base_s = smem_u32(q_base);
+    const uint32_t c = dt & 15, rb = dt >> 4;
+    const uint32_t q_off = rb * 64u + c * 4u;                       // rows rb + 16 j of word column c
+    const uint32_t sc_off = Cfg::kQTileBytes + c * 16u;             // 8 scales of word column c
+    const uint32_t z_off = Cfg::kQTileBytes + 256u + c * 4u;        // its 8 zero-points
+    using L = GemmLayoutLoaderT<1>;
+    auto fetch = [&](L& r, int qs) {
+      const uint32_t qa = q_base_s + (uint32_t)qs * Cfg::kQStageBytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r.q[j] = lds_u1(qa + q_off + (uint32_t)j * 1024u);
+      r.sc[0] = lds_u4(qa + sc_off);
+      r.zq[0] = lds_u1(qa + z_off);
+    };
+    const int nsteps = t_end - t_begin;
+    L cur, nxt;
+    cur.init();
+    nxt.init();
+    int qs = team, stage = team;       // NS, NQ even: a team keeps its parity across wrap-arounds
+    uint32_t qph = 0, phase = 0;
+    if (team < nsteps) {
+      mbar_wait(&qfull[qs], 0);
+      if (dbg && pt == 0) dbg_row[2] = tcq_timer();
+      fetch(cur, qs);
+    }
+    for (int i = team; i < nsteps; i += Cfg::kTeams) {
+      int qs_n = qs + Cfg::kTeams;
+      uint32_t qph_n = qph;
+      if (qs_n >= NQ) { qs_n -= NQ; qph_n ^= 1; }
+      if (i + Cfg::kTeams < nsteps) {     // this team's next packed words: in flight while this step is dequantised
+        mbar_wait(&qfull[qs_n], qph_n);
+        fetch(nxt, qs_n);
+      }
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (!(p.dbg & 2)) cur.store(p, 0, 0, dt, a_base_s + (uint32_t)stage * kAStageBytes);   // (timing experiment: knob 20)
+      if (!(p.dbg & 4)) fence_proxy_async_smem();   // every writer: generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&full[stage]);
+        mbar_arrive(&qempty[qs]);  // after the stores that consumed the stage's words (data dependence)
+      }
+      stage += Cfg::kTeams;
+      if (stage >= NS) { stage -= NS; phase ^= 1; }
+      cur = nxt;
+      qs = qs_n;
+      qph = qph_n;
+    }
+    if (dbg && pt == 0) dbg_row[3] = tcq_timer();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // -------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -606,6 +1002,56 @@ static cudaError_t dispatch_bt(int BT, const CUtensorMap& tm, const CUtensorMap&
   }
 }
 
+template <int BT>
+static cudaError_t launch_tcq(const CUtensorMap& tm, const CUtensorMap& tmq, const TcParams& p, cudaStream_t st) {
+  using Cfg = TcqCfg<BT>;
+  auto kern = gemm_tcq_kernel<BT>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int KS = p.K / kBK, sms = sm_count();
+  const long long T = (long long)p.n_tiles * KS;
+  long long grid = T / 4;   // balanced ranges: every CTA streams the same bytes; at least 4 k-steps per CTA
+  if (grid < 1) grid = 1;
+  if (grid > sms) grid = sms;
+  // Tile-aligned ranges for the larger token counts (knob 21: 1 = never, 2 = always): a range that never straddles an
+  // n-tile has ONE segment, and a range that is a whole tile stores fp16 directly - no fp32 REDs, no ticket, no
+  // read-back; at M >= 64 those cost more (M * 128 REDs per segment, M / 16 L2 round trips per finalised tile) than the
+  // idle SMs of an uneven cut.
+  const int mode = knob(21);
+  if (mode == 2 || (mode == 0 && p.M >= 64)) {
+    long long g = 0;
+    if (p.n_tiles <= sms) {
+      int ks = sms / p.n_tiles;
+      while (ks > 1 && (KS % ks != 0 || KS / ks < 4)) --ks;
+      g = (long long)p.n_tiles * ks;
+    } else {
+      const int tpc = (p.n_tiles + sms - 1) / sms;
+      if (p.n_tiles % tpc == 0) g = p.n_tiles / tpc;
+    }
+    if (g > 0) grid = g;
+  }
+  return launch_kernel(kern, dim3((unsigned)grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tm, tmq, p);
+}
+
+// Small-M path (M <= kTcqMaxM, GEMM layout, G >= 64, N % 128 == 0): see gemm_tcq_kernel.  The fp32 split-K scratch is
+// the caller's workspace: M * N floats fit the documented min(M, 64) * N * 8 bytes for every M <= 128.
+constexpr int kTcqMaxM = 128;
+static bool tcq_applicable(const GemmArgs& a, const float* acc_ws, const int* tickets) {
+  if (knob(19) == 1) return false;
+  if (a.M > kTcqMaxM || a.G < 64 || (a.N % kTileN) != 0 || a.N / kTileN > 4096) return false;
+  if (acc_ws == nullptr || tickets == nullptr) return false;
+  if (((reinterpret_cast<uintptr_t>(a.qweight) | reinterpret_cast<uintptr_t>(a.scales) |
+        reinterpret_cast<uintptr_t>(a.qzeros)) & 15) != 0)
+    return false;
+  return true;
+}
+
 static int zeros_width_tc(int K, int G) {
   const int mult = G >= 128 ? 1 : (G == 64 ? 2 : 4);
   int base = ((K / G) + 7) / 8;
@@ -627,6 +1073,7 @@ cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, 
   p.acc_ws = acc_ws;
   p.tickets = tickets;
   p.M = a.M; p.K = a.K; p.N = a.N; p.G = a.G;
+  p.dbg = 0;
   p.zw = zeros_width_tc(a.K, a.G);
   p.g_shift = 31;
   if (g_pow2) {
@@ -634,6 +1081,26 @@ cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, 
     while ((1 << p.g_shift) < a.G) ++p.g_shift;
   }
   p.n_tiles = (a.N + kTileN - 1) / kTileN;
+  if (layout == 0 && tcq_applicable(a, acc_ws, tickets)) {
+    const int BQ = a.M <= 16 ? 16 : (a.M <= 32 ? 32 : (a.M <= 64 ? 64 : 128));
+    CUtensorMap tmxq, tmwq;
+    p.m_tiles = 1;
+    p.ksplit = 1;
+    p.has_tmq = 1;
+    p.dbg = (knob(3) == 9 ? 1 : 0) | ((knob(20) & 15) << 1);   // knob 20: timing experiments (results invalid)
+    cudaError_t eq = make_x_tmap(a.x, a.ldx, a.M, a.K, BQ, &tmxq);
+    if (eq == cudaSuccess)
+      eq = make_tmap_2d(a.qweight, 1, (uint64_t)(a.N / 8), (uint64_t)a.K, (uint64_t)(a.N / 8) * 4, 16, kBK, &tmwq, false);
+    if (eq == cudaSuccess) {
+      switch (BQ) {
+        case 16: return launch_tcq<16>(tmxq, tmwq, p, st);
+        case 32: return launch_tcq<32>(tmxq, tmwq, p, st);
+        case 64: return launch_tcq<64>(tmxq, tmwq, p, st);
+        default: return launch_tcq<128>(tmxq, tmwq, p, st);
+      }
+    }
+    // a tensor map that cannot be encoded: fall through to the register-staged kernel
+  }
   p.m_tiles = (a.M + BT - 1) / BT;
   const int KS = a.K / kBK;
   int ksplit = 1;

@@ -75,6 +75,7 @@ cudaError_t gemv_fast_layout(const FastArgs& a, cudaStream_t st);
 
 // tensor-core path; layout: 0 = GEMM, 1 = GEMV, 2 = FAST (qweight/qzeros reinterpretations documented in gemm_tc.cu)
 cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, cudaStream_t st);
+cudaError_t gemm_tcq_debug_read(void* dst, size_t bytes);   // phase timestamps of the last small-M launch (knob 3 == 9)
 
 // decode program (program.cu)
 struct Program;

@@ -128,6 +128,9 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *          CTA, aborted} of the first wait that exceeded 0.5 s (every spin loop of that kernel gives up rather than
  *          hang the GPU), then per CTA 10 ints = (code << 16 | op) of the wait each warp abandoned;
  *          4 = the decode-program kernel does not recycle its accumulator rows (inspection with tools/program_debug.py)
+ *          9 = the small-M tensor-core kernel (9 <= M <= 128, GEMM layout) records per-CTA phase timestamps
+ *          (b200awq_debug_read returns [cta][8] uint64 ns: entry, setup done, first packed stage landed, producers
+ *          done, MMA issuer done, last accumulator drained, epilogue done, number of segments)
  *   key 4: 1 = launch every kernel with the programmatic-dependent-launch attribute (the kernels issue
  *          their weight loads before griddepcontrol.wait, so consecutive linears overlap); default 0
  *   key 5: 1 = disable the persistent TMA-ring GEMV (use the register-staged GEMV for every M <= 8 shape)
@@ -151,6 +154,13 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *   key 16: decode-program watchdog in seconds (0 = the default 0.5 s): every spin of the program kernels gives up
  *           after this long; raise it under compute-sanitizer / a debugger, where kernels run orders of magnitude slower
  *   key 15: 1 = wrap every launching entry point in an NVTX range named after it (profiler timelines); default 0
+ *   key 19: 1 = never use the small-M kernel with TMA-staged packed weights (gemm_tcq_kernel; default: every GEMM-layout
+ *           call with 9 <= M <= 128 (or M above key 2's threshold), G >= 64, N % 128 == 0 runs it)
+ *   key 20: small-M kernel timing experiments (outputs are WRONG while set): bit 0 = producers skip the dequantisation and
+ *           the shared-memory stores, bit 1 = producers skip the generic->async proxy fence, bit 2 = no MMA is
+ *           issued (commits only), bit 3 = one MMA per k-step instead of four
+ *   key 21: small-M kernel work cut: 0 = balanced (n-tile, k-step) ranges below 64 tokens, tile-aligned ranges from 64 tokens
+ *           (no straddling segments, whole tiles store directly); 1 = always balanced; 2 = always tile-aligned
  *   key 14: decode program kind (read at b200awq_program_create): 0 = stream variant when the sequence fits it,
  *           else the split-K kernel; 1 = split-K kernel only; 2 = stream variant only
  */

@@ -394,3 +394,64 @@ def test_persistent_gemv_is_bit_reproducible(ext):
         torch.cuda.synchronize()
         for ws in e._WS.values():
             assert int(ws.view(torch.int32).ne(0).sum()) == 0
+
+
+# ------------------------------------------------ small-M tensor-core kernel (TMA-staged packed weights, 9 <= M <= 128)
+TCQ_CASES = [
+    # K, N, G        (N % 128 == 0, G >= 64: the envelope of gemm_tcq_kernel; everything else keeps the register-staged kernel)
+    (512, 256, 64), (1152, 384, 128), (2048, 640, -1), (1024, 1792, 128), (4096, 128, 128), (4096, 4096, 128),
+]
+
+
+@pytest.mark.parametrize("K,N,G", TCQ_CASES)
+def test_small_m_tma_staged_kernel(ext, K, N, G):
+    """Range-partitioned split-K over (n-tile, k-step), every token-tile width (16 / 32 / 64 / 128), ragged M, bias,
+    odd numbers of k-steps and n-tiles, one group per row (G = K); against the oracle, against the register-staged
+    kernel (knob 19 = 1), and the scratch must be all-zero after every call."""
+    from autoawq_b200 import ext as e
+
+    c = O.make_case(K, N, G, seed=K % 31 + N % 29)
+    Gs = c["group_size"]
+    w = O.dequantize_gemm(c["qweight"], c["qzeros"], c["scales"], Gs)
+    rng = np.random.default_rng(7)
+    b = (rng.standard_normal(N) * 0.5).astype(np.float16)
+    qw, qz, sc, bt = _t(c["qweight"]), _t(c["qzeros"]), _t(c["scales"]), _t(b)
+    Ms = (9, 16, 17, 32, 33, 64, 100, 128) if K * N <= 2048 * 2048 else (16, 40, 128)
+    for M in Ms:
+        x = rng.standard_normal((M, K)).astype(np.float16)
+        xt = _t(x)
+        ref = O.gemm_f64(x, w) + b.astype(np.float64)
+        y = e.linear_forward("gemm", xt, qw, sc, qz, Gs, bt)
+        _close(y.cpu().numpy(), ref, _budget(x, w), WR_TC, f"tcq K={K} N={N} G={Gs} M={M}")
+        y2 = e.linear_forward("gemm", xt, qw, sc, qz, Gs, bt)     # scratch restored: same result up to fp32 order
+        assert torch.allclose(y2.float(), y.float(), rtol=2e-3, atol=1e-3)
+        e.set_knob(19, 1)
+        try:
+            yo = e.linear_forward("gemm", xt, qw, sc, qz, Gs, bt)
+        finally:
+            e.set_knob(19, 0)
+        _close(yo.cpu().numpy(), ref, _budget(x, w), WR_TC, f"register-staged K={K} N={N} M={M}")
+    torch.cuda.synchronize()
+    for ws in e._WS.values():
+        assert int(ws.view(torch.int32).ne(0).sum()) == 0, "split-K scratch not restored"
+
+
+def test_small_m_kernel_below_nine_tokens(ext):
+    """With the GEMV threshold (knob 2) at 0 the same kernel serves M = 1 .. 8 (16-token tile, rows past M zero-filled
+    by TMA): exact dequantised A tile, so the tensor-core tolerance applies."""
+    from autoawq_b200 import ext as e
+
+    K, N, G = 2048, 768, 128
+    c = O.make_case(K, N, G, seed=5)
+    w = O.dequantize_gemm(c["qweight"], c["qzeros"], c["scales"], G)
+    rng = np.random.default_rng(9)
+    qw, qz, sc = _t(c["qweight"]), _t(c["qzeros"]), _t(c["scales"])
+    prev = e.get_knob(2)
+    e.set_knob(2, 0)
+    try:
+        for M in (1, 3, 8):
+            x = rng.standard_normal((M, K)).astype(np.float16)
+            y = e.linear_forward("gemm", _t(x), qw, sc, qz, G).cpu().numpy()
+            _close(y, O.gemm_f64(x, w), _budget(x, w), WR_TC, f"tcq M={M}")
+    finally:
+        e.set_knob(2, prev)

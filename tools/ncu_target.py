@@ -62,7 +62,7 @@ if what == "layer":
     sys.exit(0)
 K, N, M = {"gemv": (4096, 4096, 1), "gemv_big": (4096, 28672, 1), "gemm": (4096, 4096, 4096),
            "gemm64": (4096, 14336, 64), "gemm16": (4096, 4096, 16), "gemv8": (4096, 4096, 8),
-           "prefill_big": (4096, 14336, 4096)}[what]
+           "prefill_big": (4096, 14336, 4096), "gemm16_big": (4096, 28672, 16), "gemm64_big": (4096, 28672, 64)}[what]
 G = 128
 wbytes = K * N // 2
 nbuf = max(3, int(400e6 // wbytes) + 1)
