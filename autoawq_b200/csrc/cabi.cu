@@ -124,7 +124,12 @@ int b200awq_gemm_forward(const void* x, int64_t ldx, const int32_t* qweight, con
   Ws ws;
   const bool have_ws = carve(workspace, workspace_bytes, M, N, &ws);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (M <= knob(2) && M <= 8 && gemv_gemm_layout_supported(a)) {
+  // M <= 8 (knob 2): the persistent TMA-ring GEMV.  At its default the threshold drops to 4 where the small-M tensor-core
+  // kernel applies: from 5 tokens on it is faster on every Llama shape (profiles/r02_tcq_sweep.json: 13 vs 20 us on
+  // 4096 x 4096, 33 vs 47 us on 4096 x 28672 at M = 8; at M = 4 the GEMV still wins on three of four shapes).
+  int gemv_max = knob(2);
+  if (gemv_max == 8 && M > 4 && have_ws && gemm_tcq_applicable(a, ws.acc, ws.tickets)) gemv_max = 4;
+  if (M <= gemv_max && M <= 8 && gemv_gemm_layout_supported(a)) {
     if (!have_ws) return B200AWQ_EWORKSPACE;  // the GEMV splits K across CTAs
     if ((N + 255) / 256 > 4096) return B200AWQ_EUNSUPPORTED;
     if (knob(5) == 0 && gemv_v3_supported(a)) return fold(gemv_v3(a, ws.acc, ws.tickets, st));

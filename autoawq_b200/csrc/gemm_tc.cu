@@ -512,40 +512,44 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
 // ------------------------------------------------------------ small-M kernel (TMA-staged packed weights)
 // M <= 128 on the GEMM layout is HBM-bound; the kernel above is latency-bound there (its producers pull the packed
 // words L2 -> registers through a 6-deep ring: ~500-900 clk per k-step whatever the token count, r2 M sweep).  This
-// variant keeps the MMA / descriptor / epilogue machinery and changes the three things that bound it:
-//   * the packed weights of a k-step (4 KB tile + the group's 256 B of scales + 64 B of zeros) arrive by TMA in a
-//     deep shared-memory ring (kNQ = 20..28 stages ~ 100 KB in flight per SM, independent of registers), issued by a
-//     dedicated warp that never waits for activations (weights do not depend on the predecessor kernel);
-//   * the producers read a stage with conflict-free LDS, dequantise exactly as before (bit-identical A tile) and run
-//     one k-step ahead of their own stores;
-//   * work is cut into CONTIGUOUS RANGES of the linearised (n-tile, k-step) sequence, one range per SM: every SM
+// variant keeps the MMA / descriptor / epilogue machinery and changes what bounded it:
+//   * the packed weights arrive by TMA in a deep shared-memory ring, one stage = a PAIR of k-steps (128 rows x 16 words
+//     = 8 KB, plus the rows' group constants: 256 B of scales + 64 B of zeros per group), 11-14 stages = 96-123 KB in
+//     flight per SM independent of registers (a read-only probe with the same ring moves 2.5 TB/s with 64 KB in flight
+//     and 3.9 TB/s with 128 KB: profiles/r02_membw_box_shapes.log), issued by a dedicated warp that never waits for
+//     activations (weights do not depend on the predecessor kernel);
+//   * two producer teams of 8 warps: team t dequantises rows 64 t .. 64 t + 63 of every stage (conflict-free LDS, the
+//     exact arithmetic of the dequant kernel: the A tile is bit-identical), one step ahead of its own stores, into its own
+//     A stages; the activation tiles have their own ring (they come from L2 with ~1 us of latency);
+//   * the MMA / TMA issue loops are walked by the whole warp with one elected lane issuing (uniform operands);
+//   * work is cut into CONTIGUOUS RANGES of the linearised (n-tile, k-step pair) sequence, one range per SM: every SM
 //     streams the same number of bytes whatever N / 128 is (the (tile, k-split) items of the kernel above leave
 //     224 tiles on 148 SMs two waves deep).  A range crosses at most a few n-tiles = segments; a segment that holds a
 //     whole K column stores fp16 directly, a partial one adds fp32 into the caller's zeroed workspace and bumps the
-//     tile's ticket by its number of k-steps; the contributor that completes K rounds, adds the bias, restores zeros.
+//     tile's ticket by its number of k-step pairs; the contributor that completes K rounds, adds the bias, restores
+//     zeros.  From 64 tokens on the ranges are tile-aligned instead (launch_tcq).
 template <int BT>
 struct TcqCfg {
-  static constexpr int kNS = BT <= 32 ? 6 : 4;                             // A stages (producers -> MMA); even
-  static constexpr int kNX = BT <= 16 ? 16 : (BT <= 64 ? 8 : 5);  // X stages (TMA -> MMA), own ring
-  static constexpr int kNQ = BT <= 64 ? 20 : 16;                           // packed-weight stages (TMA -> producers); even
+  static constexpr int kNS = 4;                                            // A stages (producers -> MMA), 2 per team
+  static constexpr int kNX = BT <= 16 ? 16 : (BT == 32 ? 8 : (BT == 64 ? 8 : 4));   // X stages (TMA -> MMA), own ring
+  static constexpr int kNQ = BT <= 32 ? 14 : 11;                           // packed-weight stages (TMA -> producers)
   static constexpr int kXStageBytes = BT * kBK * 2;
-  static constexpr int kQTileBytes = 16 * 4 * kBK;                         // 64 rows x 16 words
-  static constexpr int kQTxBytes = kQTileBytes + 256 + 64;                 // + scales of 128 columns + zeros of 16 words
-  static constexpr int kQStageBytes = 4480;                                // padded to a multiple of 128
+  static constexpr int kQRows = 2 * kBK;                                   // rows per packed stage: one k-step per team
+  static constexpr int kQTileBytes = 16 * 4 * kQRows;                      // 128 rows x 16 words = 8 KB
+  static constexpr int kQStageBytes = kQTileBytes + 2 * 256 + 2 * 64 + 128;   // up to 2 groups of constants; 128-B multiple
   static constexpr int kAccCols = BT < 32 ? 32 : BT;
-  // Independent accumulators per buffer: the k16 slices of a k-step go to accumulator k16 % kNAcc and the epilogue adds
-  // them.  A 128 x BT x 16 MMA with BT <= 128 retires in a few clocks of tensor-pipe time but ~130 clk after issue, and
-  // MMAs into ONE accumulator serialise on that latency (4 x 130 clk per k-step = the measured 275 ns of the third
-  // version, whatever BT); separate accumulators pipeline.
-  static constexpr int kNAcc = BT <= 64 ? 4 : 2;
-  static constexpr int kTmemCols = 2 * kNAcc * kAccCols;
+  static constexpr int kTeams = 2;
+  // One MMA-issuing warp per team, each with its own accumulator (the epilogue adds the two): the issue loop of ONE
+  // warp (two barrier waits, descriptor arithmetic on the uniform datapath, 4 MMAs, 2 commits: ~55 dependent
+  // instructions) takes ~300 ns per k-step however little the tensor pipe has to do - with every other stage removed
+  // (no dequantisation, no MMAs) the kernel still ran at that pace (profiles/r02_tcq_experiments.md).
+  static constexpr int kTmemCols = 2 * kTeams * kAccCols;                  // two buffers x one accumulator per team
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation: power of two <= 512");
-  static constexpr int kTeams = 2;       // producer teams of 8 warps: team t dequantises k-steps t, t + 2, ...
-  static constexpr int kQWarps = 2;      // Q-TMA warps: warp w issues the bulk copies of k-steps w, w + 2, ... (3 would cap registers at 72: spills)
-  static constexpr int kThreads = 192 + 256 * kTeams + 32 * kQWarps;   // X-TMA, MMA, 4 epilogue, 16 producer warps, 2 Q-TMA
+  static constexpr int kThreads = 192 + 256 * kTeams + 64;   // X-TMA, MMA 0, 4 epilogue, 16 producer warps, Q-TMA, MMA 1
   static constexpr size_t kSmemBytes = (size_t)kNS * kAStageBytes + (size_t)kNX * kXStageBytes +
                                        (size_t)kNQ * kQStageBytes + 1024 /*align slack*/ + 1024 /*barriers*/;
-  static_assert(kNS >= kTeams && kNQ >= kTeams && kNQ >= kQWarps, "a ring index wraps at most once per advance");
+  static_assert(kNS % kTeams == 0 && kNX % kTeams == 0, "team t owns A stages / X stages t, t + 2, ...");
+  static_assert(kQStageBytes % 128 == 0, "TMA destination alignment");
   static_assert(kSmemBytes <= 232448, "shared memory per CTA");
 };
 
@@ -573,6 +577,7 @@ cudaError_t gemm_tcq_debug_read(void* dst, size_t bytes) {
   return cudaMemcpyFromSymbol(dst, g_tcq_dbg, bytes < sizeof(g_tcq_dbg) ? bytes : sizeof(g_tcq_dbg));
 }
 
+// Work unit = a PAIR of k-steps (128 rows of one 128-column tile); p.K % 128 == 0.
 template <int BT>
 __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
     gemm_tcq_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq, const TcParams p) {
@@ -582,14 +587,14 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_base = smem;                                              // NS x 16 KB
   uint8_t* x_base = a_base + (size_t)NS * kAStageBytes;                // NX x BT*128 B
-  uint8_t* q_base = x_base + (size_t)NX * Cfg::kXStageBytes;           // NQ x 4480 B
+  uint8_t* q_base = x_base + (size_t)NX * Cfg::kXStageBytes;           // NQ x kQStageBytes
   uint64_t* bars = reinterpret_cast<uint64_t*>(q_base + (size_t)NQ * Cfg::kQStageBytes);
   uint64_t* full = bars;                     // [NS]  8 producer warps (one team)
   uint64_t* empty = full + NS;               // [NS]  tcgen05.commit
   uint64_t* xfull = empty + NS;              // [NX]  expect_tx of the activation tile
   uint64_t* xempty = xfull + NX;             // [NX]  tcgen05.commit
   uint64_t* qfull = xempty + NX;             // [NQ]  expect_tx of the packed stage
-  uint64_t* qempty = qfull + NQ;             // [NQ]  8 producer warps (one team)
+  uint64_t* qempty = qfull + NQ;             // [NQ]  16 producer warps (both teams)
   uint64_t* tmem_full = qempty + NQ;         // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
@@ -615,10 +620,10 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
     }
     for (int s = 0; s < NQ; ++s) {
       mbar_init(&qfull[s], 1);
-      mbar_init(&qempty[s], 8);
+      mbar_init(&qempty[s], 8 * Cfg::kTeams);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_full[b], Cfg::kTeams);   // one commit per MMA warp
       mbar_init(&tmem_empty[b], 128);
     }
     fence_mbar_init();
@@ -633,56 +638,59 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
   if (dbg && threadIdx.x == 0) dbg_row[1] = tcq_timer();
 
-  // this CTA's contiguous range of the linearised (n-tile, k-step) sequence
-  const int KS = p.K / kBK;
-  const long long T = (long long)p.n_tiles * KS;
+  // this CTA's contiguous range of the linearised (n-tile, k-step pair) sequence
+  const int KP = p.K / Cfg::kQRows;   // k-step pairs per tile
+  const long long T = (long long)p.n_tiles * KP;
   const int t_begin = (int)(T * (long long)blockIdx.x / (long long)gridDim.x);
   const int t_end = (int)(T * (long long)(blockIdx.x + 1) / (long long)gridDim.x);
   constexpr int kQWarp = 6 + 8 * Cfg::kTeams;
+  // groups of constants per packed stage: G = 64 -> one per k-step; G >= 128 (or one group per row) -> one per pair
+  const int ng = p.g_shift == 6 ? 2 : 1;
 
-  if (warp >= kQWarp) {
+  if (warp == kQWarp) {
     // ================================================================= Q-TMA: packed weights + group constants
-    // kQWarps warps, warp w owns k-steps w, w + kQWarps, ... of the CTA's range: ONE warp issuing the three bulk copies of
-    // every step (wait, expect_tx, tensor tile, scales, zeros: ~500 clk of dependent uniform-datapath work) was the
-    // k-step time of the second version - its ring was never full while the producers waited for data (ncu source page).
-    // The whole warp walks the loop, one elected lane issues: uniform operands, no per-instruction retry loops.
+    // (the whole warp walks the loop, one elected lane issues: uniform operands, no per-instruction retry loops)
     {
       const bool leader = elect_one();
-      const int qw = warp - kQWarp;
       const uint32_t NW = (uint32_t)p.N >> 3;
-      const int nsteps = t_end - t_begin;
-      int nt = (t_begin + qw) / KS, sk = (t_begin + qw) - nt * KS;
-      int qs = qw;            // kQWarps <= NQ
+      const uint32_t tx = (uint32_t)Cfg::kQTileBytes + (uint32_t)ng * 320u;
+      int qs = 0;
       uint32_t qph = 0;
-      for (int i = qw; i < nsteps; i += Cfg::kQWarps) {
-        mbar_wait(&qempty[qs], qph ^ 1);
-        uint8_t* dst = q_base + (size_t)qs * Cfg::kQStageBytes;
-        const uint32_t g = (uint32_t)(sk * kBK) >> p.g_shift;
-        if (leader) {
-          mbar_arrive_expect_tx(&qfull[qs], Cfg::kQTxBytes);
-          tma_load_2d(dst, &tmq, &qfull[qs], nt * 16, sk * kBK);
-          bulk_load_1d(dst + Cfg::kQTileBytes, p.scales + (size_t)g * p.N + (size_t)nt * kTileN, 256, &qfull[qs]);
-          bulk_load_1d(dst + Cfg::kQTileBytes + 256, p.qzeros + (size_t)g * NW + (size_t)nt * 16, 64, &qfull[qs]);
+      for (int t = t_begin; t < t_end;) {
+        const int nt = t / KP, d0 = t - nt * KP;
+        const int d1 = (KP - d0 < t_end - t) ? KP : d0 + (t_end - t);
+        for (int d = d0; d < d1; ++d) {
+          mbar_wait(&qempty[qs], qph ^ 1);
+          uint8_t* dst = q_base + (size_t)qs * Cfg::kQStageBytes;
+          const uint32_t g = (uint32_t)(d * Cfg::kQRows) >> p.g_shift;
+          if (leader) {
+            mbar_arrive_expect_tx(&qfull[qs], tx);
+            tma_load_2d(dst, &tmq, &qfull[qs], nt * 16, d * Cfg::kQRows);
+            for (int h = 0; h < ng; ++h) {
+              bulk_load_1d(dst + Cfg::kQTileBytes + h * 256, p.scales + (size_t)(g + h) * p.N + (size_t)nt * kTileN, 256,
+                           &qfull[qs]);
+              bulk_load_1d(dst + Cfg::kQTileBytes + 512 + h * 64, p.qzeros + (size_t)(g + h) * NW + (size_t)nt * 16, 64,
+                           &qfull[qs]);
+            }
+          }
+          __syncwarp();
+          if (++qs == NQ) { qs = 0; qph ^= 1; }
         }
-        __syncwarp();
-        qs += Cfg::kQWarps;
-        if (qs >= NQ) { qs -= NQ; qph ^= 1; }
-        sk += Cfg::kQWarps;
-        while (sk >= KS) { sk -= KS; ++nt; }
+        t += d1 - d0;
       }
     }
   } else if (warp == 0) {
     // ================================================================= X-TMA: activation tiles, own ring (the tiles
-    // come from L2 with ~1 us of latency: tying them to the NS A stages made that latency the k-step time)
+    // come from L2 with ~1 us of latency: tying them to the A stages made that latency the k-step time)
     {
       const bool leader = elect_one();
       pdl_wait();  // the activations are the predecessor's output
       int xs = 0;
       uint32_t xph = 0;
       for (int t = t_begin; t < t_end;) {
-        const int nt = t / KS, s0 = t - nt * KS;
-        const int s1 = (KS - s0 < t_end - t) ? KS : s0 + (t_end - t);
-        for (int s = s0; s < s1; ++s) {
+        const int nt = t / KP, d0 = t - nt * KP;
+        const int d1 = (KP - d0 < t_end - t) ? KP : d0 + (t_end - t);
+        for (int s = 2 * d0; s < 2 * d1; ++s) {
           mbar_wait(&xempty[xs], xph ^ 1);
           if (leader) {
             mbar_arrive_expect_tx(&xfull[xs], Cfg::kXStageBytes);
@@ -691,35 +699,37 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
           __syncwarp();
           if (++xs == NX) { xs = 0; xph ^= 1; }
         }
-        t += s1 - s0;
+        t += d1 - d0;
       }
     }
-  } else if (warp == 1) {
-    // ================================================================= MMA issuer
+  } else if (warp == 1 || warp == kQWarp + 1) {
+    // ================================================================= MMA issuers (warp 1: team 0, last warp: team 1)
     // The WHOLE warp walks the loop (waits, stage bookkeeping, descriptors) and one elected lane issues: everything the
     // tcgen05 instructions consume is then warp-uniform for the compiler (uniform registers).  Under `if (lane == 0)`
     // the same operands are divergent values, and every UTCHMMA / UTCBAR came wrapped in an ELECT + 5 x R2UR + retry
     // loop: ~130 instructions and ~700 clk per k-step on ONE thread - the k-step time of the first version (ncu source
     // page: the producers' top stall was the wait for the MMA's stage release).
+    // MMA warp w serves team w: k-step w of every pair (A stages w, w + 2; X stages w, w + 2, ...), accumulator w.
     {
       constexpr uint32_t idesc = umma_idesc_f16(kTileN, BT, 1, 0);
+      const int mw = warp == 1 ? 0 : 1;
       const bool leader = elect_one();
       const int mma_per_step = (p.dbg & 8) ? 0 : ((p.dbg & 16) ? 1 : kBK / 16);
       const uint32_t a_base_s = smem_u32(a_base), x_base_s = smem_u32(x_base);
       const uint64_t da0 = umma_smem_desc(a_base_s, 8192, 1024);   // MN-major SW128; start address in bits [0, 14)
       const uint64_t db0 = umma_smem_desc(x_base_s, 16, 1024);     // K-major SW128
-      int stage = 0, xs = 0;
+      int stage = mw, xs = mw;
       uint32_t phase = 0, xph = 0;
       int it = 0;
       for (int t = t_begin; t < t_end; ++it) {
-        const int nt = t / KS, s0 = t - nt * KS;
-        const int s1 = (KS - s0 < t_end - t) ? KS : s0 + (t_end - t);
+        const int nt = t / KP, d0 = t - nt * KP;
+        const int d1 = (KP - d0 < t_end - t) ? KP : d0 + (t_end - t);
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&tmem_empty[buf], use ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * Cfg::kNAcc * Cfg::kAccCols);
-        for (int s = s0; s < s1; ++s) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)((buf * Cfg::kTeams + mw) * Cfg::kAccCols);
+        for (int d = d0; d < d1; ++d) {
           mbar_wait(&xfull[xs], xph);
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -730,20 +740,22 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
 #pragma unroll
             for (int k16 = 0; k16 < kBK / 16; ++k16)
               if (k16 < mma_per_step)   // (4 unless a timing experiment is on: knob 20)
-                umma_f16_ss(d_tmem + (uint32_t)((k16 % Cfg::kNAcc) * Cfg::kAccCols), da + (uint64_t)(k16 * (2048 >> 4)),
-                            db + (uint64_t)(k16 * (32 >> 4)), idesc, (s > s0 || k16 >= Cfg::kNAcc) ? 1u : 0u);
+                umma_f16_ss(d_tmem, da + (uint64_t)(k16 * (2048 >> 4)), db + (uint64_t)(k16 * (32 >> 4)), idesc,
+                            (d > d0 || k16 > 0) ? 1u : 0u);
             umma_commit(&empty[stage]);
             umma_commit(&xempty[xs]);
           }
           __syncwarp();
-          if (++stage == NS) { stage = 0; phase ^= 1; }
-          if (++xs == NX) { xs = 0; xph ^= 1; }
+          stage += Cfg::kTeams;
+          if (stage >= NS) { stage -= NS; phase ^= 1; }
+          xs += Cfg::kTeams;
+          if (xs >= NX) { xs -= NX; xph ^= 1; }
         }
         if (leader) umma_commit(&tmem_full[buf]);
         __syncwarp();
-        t += s1 - s0;
+        t += d1 - d0;
       }
-      if (dbg && leader) { dbg_row[4] = tcq_timer(); dbg_row[7] = (unsigned long long)it; }
+      if (dbg && leader && mw == 0) { dbg_row[4] = tcq_timer(); dbg_row[7] = (unsigned long long)it; }
     }
   } else if (warp < 6) {
     // ================================================================= epilogue (4 warps)
@@ -752,42 +764,33 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
     pdl_wait();                       // outputs / workspace may alias memory the predecessor still uses
     int it = 0;
     for (int t = t_begin; t < t_end; ++it) {
-      const int nt = t / KS, s0 = t - nt * KS;
-      const int s1 = (KS - s0 < t_end - t) ? KS : s0 + (t_end - t);
-      const bool whole = (s0 == 0 && s1 == KS);
+      const int nt = t / KP, d0 = t - nt * KP;
+      const int d1 = (KP - d0 < t_end - t) ? KP : d0 + (t_end - t);
+      const bool whole = (d0 == 0 && d1 == KP);
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&tmem_full[buf], use);
       tc_fence_after();
       const int n = nt * kTileN + q4 * 32 + lane;   // N % 128 == 0: always in range
       const float bias_v = p.bias != nullptr ? __half2float(p.bias[n]) : 0.f;
-      const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * Cfg::kNAcc * Cfg::kAccCols);
+      const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * Cfg::kTeams * Cfg::kAccCols);
 #pragma unroll 1
       for (int c0 = 0; c0 < BT; c0 += 16) {
-        // the kNAcc partial accumulators of 16 tokens, added in a fixed order
+        // the two teams' accumulators of 16 tokens, added in a fixed order
         uint32_t v[16], w[16];
-        float f[16];
         tmem_ld_32x16(tbuf + (uint32_t)c0, v);
         tmem_ld_32x16(tbuf + (uint32_t)(Cfg::kAccCols + c0), w);
         tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
-        if constexpr (Cfg::kNAcc == 4) {
-          tmem_ld_32x16(tbuf + (uint32_t)(2 * Cfg::kAccCols + c0), v);
-          tmem_ld_32x16(tbuf + (uint32_t)(3 * Cfg::kAccCols + c0), w);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
-        }
         if (c0 < p.M) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int m = c0 + j;
             if (m < p.M) {
+              const float f = __uint_as_float(v[j]) + __uint_as_float(w[j]);
               if (whole)
-                p.y[(int64_t)m * p.N + n] = __float2half_rn(f[j] + bias_v);
+                p.y[(int64_t)m * p.N + n] = __float2half_rn(f + bias_v);
               else
-                red_add_f32(&p.acc_ws[(int64_t)m * p.N + n], f[j]);
+                red_add_f32(&p.acc_ws[(int64_t)m * p.N + n], f);
             }
           }
         }
@@ -799,8 +802,8 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
         // relaxed REDs -> CTA-scope barrier -> one acq_rel ticket (release is cumulative over what the barrier ordered)
         named_bar_sync(1, 128);
         if (et == 0) {
-          const int prev = atom_add_acq_rel(&p.tickets[nt], s1 - s0);
-          *s_flag = (prev + (s1 - s0) == KS);
+          const int prev = atom_add_acq_rel(&p.tickets[nt], d1 - d0);
+          *s_flag = (prev + (d1 - d0) == KP);
         }
         named_bar_sync(1, 128);
         const bool last = *s_flag != 0;
@@ -824,22 +827,23 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
           if (et == 0) p.tickets[nt] = 0;
         }
       }
-      t += s1 - s0;
+      t += d1 - d0;
     }
     if (dbg && et == 0) dbg_row[6] = tcq_timer();
   } else {
     // ================================================================= dequant producers (2 teams x 8 warps)
-    // Team t owns k-steps t, t + 2, ... of the CTA's range (A stage i % NS, packed stage i % NQ): the two teams'
-    // [wait, LDS, dequant, STS, proxy fence, arrive] chains overlap, so the chain's latency is paid once per two steps.
+    // Team t owns k-step t of every packed stage (rows 64 t ..): A stages t, t + 2.  The two teams' [wait, LDS, dequant,
+    // STS, proxy fence, arrive] chains overlap.
     const int pt = threadIdx.x - 192;
     const int team = pt >> 8;
     const int dt = pt & 255;  // 0..255 within the team
     const uint32_t a_base_s = smem_u32(a_base);
     const uint32_t q_base_s = smem_u32(q_base);
     const uint32_t c = dt & 15, rb = dt >> 4;
-    const uint32_t q_off = rb * 64u + c * 4u;                       // rows rb + 16 j of word column c
-    const uint32_t sc_off = Cfg::kQTileBytes + c * 16u;             // 8 scales of word column c
-    const uint32_t z_off = Cfg::kQTileBytes + 256u + c * 4u;        // its 8 zero-points
+    const uint32_t q_off = ((uint32_t)team * kBK + rb) * 64u + c * 4u;    // rows 64 team + rb + 16 j of word column c
+    const uint32_t gh = ng == 2 ? (uint32_t)team : 0u;                      // which group of constants of the stage
+    const uint32_t sc_off = Cfg::kQTileBytes + gh * 256u + c * 16u;         // 8 scales of word column c
+    const uint32_t z_off = Cfg::kQTileBytes + 512u + gh * 64u + c * 4u;     // its 8 zero-points
     using L = GemmLayoutLoaderT<1>;
     auto fetch = [&](L& r, int qs) {
       const uint32_t qa = q_base_s + (uint32_t)qs * Cfg::kQStageBytes;
@@ -848,22 +852,21 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
       r.sc[0] = lds_u4(qa + sc_off);
       r.zq[0] = lds_u1(qa + z_off);
     };
-    const int nsteps = t_end - t_begin;
+    const int npairs = t_end - t_begin;
     L cur, nxt;
     cur.init();
     nxt.init();
-    int qs = team, stage = team;       // NS, NQ even: a team keeps its parity across wrap-arounds
+    int qs = 0, stage = team;
     uint32_t qph = 0, phase = 0;
-    if (team < nsteps) {
-      mbar_wait(&qfull[qs], 0);
+    if (npairs > 0) {
+      mbar_wait(&qfull[0], 0);
       if (dbg && pt == 0) dbg_row[2] = tcq_timer();
-      fetch(cur, qs);
+      fetch(cur, 0);
     }
-    for (int i = team; i < nsteps; i += Cfg::kTeams) {
-      int qs_n = qs + Cfg::kTeams;
-      uint32_t qph_n = qph;
-      if (qs_n >= NQ) { qs_n -= NQ; qph_n ^= 1; }
-      if (i + Cfg::kTeams < nsteps) {     // this team's next packed words: in flight while this step is dequantised
+    for (int i = 0; i < npairs; ++i) {
+      const int qs_n = (qs + 1 == NQ) ? 0 : qs + 1;
+      const uint32_t qph_n = (qs + 1 == NQ) ? (qph ^ 1) : qph;
+      if (i + 1 < npairs) {     // the next stage's packed words: in flight while this step is dequantised
         mbar_wait(&qfull[qs_n], qph_n);
         fetch(nxt, qs_n);
       }
@@ -1014,23 +1017,28 @@ static cudaError_t launch_tcq(const CUtensorMap& tm, const CUtensorMap& tmq, con
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const int KS = p.K / kBK, sms = sm_count();
-  const long long T = (long long)p.n_tiles * KS;
-  long long grid = T / 4;   // balanced ranges: every CTA streams the same bytes; at least 4 k-steps per CTA
+  const int KP = p.K / Cfg::kQRows, sms = sm_count();   // work unit: a pair of k-steps
+  const long long T = (long long)p.n_tiles * KP;
+  long long grid = T / 2;   // balanced ranges: every CTA streams the same bytes; at least 2 pairs per CTA
   if (grid < 1) grid = 1;
   if (grid > sms) grid = sms;
-  // Tile-aligned ranges for the larger token counts (knob 21: 1 = never, 2 = always): a range that never straddles an
-  // n-tile has ONE segment, and a range that is a whole tile stores fp16 directly - no fp32 REDs, no ticket, no
-  // read-back; at M >= 64 those cost more (M * 128 REDs per segment, M / 16 L2 round trips per finalised tile) than the
-  // idle SMs of an uneven cut.
+  // Tile-aligned ranges (knob 21: 1 = never, 2 = always): a range that never straddles an n-tile has ONE segment, and a
+  // range that is a whole tile stores fp16 directly - no fp32 REDs, no ticket, no read-back (M * 128 REDs per segment,
+  // M / 16 L2 round trips per finalised tile).
   const int mode = knob(21);
-  if (mode == 2 || (mode == 0 && p.M >= 64)) {
+  if (mode != 1) {
     long long g = 0;
     if (p.n_tiles <= sms) {
+      // every tile is cut into ks ranges (boundaries b * KP / ks never cross a tile since the grid is a multiple of
+      // n_tiles); ks = 1 stores whole tiles directly.  Measured better than the balanced cut at every M <= 128 on the
+      // shapes with N / 128 <= 148 (profiles/r02_tcq_sweep.json).
       int ks = sms / p.n_tiles;
-      while (ks > 1 && (KS % ks != 0 || KS / ks < 4)) --ks;
+      if (ks > KP / 2) ks = KP / 2;
+      if (ks < 1) ks = 1;
       g = (long long)p.n_tiles * ks;
-    } else {
+    } else if (mode == 2 || p.M >= 64) {
+      // more tiles than SMs: whole tiles per CTA when they divide evenly (224 tiles -> 112 CTAs x 2); below 64 tokens
+      // the balanced cut wins there (all 148 SMs stream, the split-K traffic is small)
       const int tpc = (p.n_tiles + sms - 1) / sms;
       if (p.n_tiles % tpc == 0) g = p.n_tiles / tpc;
     }
@@ -1042,9 +1050,9 @@ static cudaError_t launch_tcq(const CUtensorMap& tm, const CUtensorMap& tmq, con
 // Small-M path (M <= kTcqMaxM, GEMM layout, G >= 64, N % 128 == 0): see gemm_tcq_kernel.  The fp32 split-K scratch is
 // the caller's workspace: M * N floats fit the documented min(M, 64) * N * 8 bytes for every M <= 128.
 constexpr int kTcqMaxM = 128;
-static bool tcq_applicable(const GemmArgs& a, const float* acc_ws, const int* tickets) {
+bool gemm_tcq_applicable(const GemmArgs& a, const float* acc_ws, const int* tickets) {
   if (knob(19) == 1) return false;
-  if (a.M > kTcqMaxM || a.G < 64 || (a.N % kTileN) != 0 || a.N / kTileN > 4096) return false;
+  if (a.M > kTcqMaxM || a.G < 64 || (a.K % 128) != 0 || (a.N % kTileN) != 0 || a.N / kTileN > 4096) return false;
   if (acc_ws == nullptr || tickets == nullptr) return false;
   if (((reinterpret_cast<uintptr_t>(a.qweight) | reinterpret_cast<uintptr_t>(a.scales) |
         reinterpret_cast<uintptr_t>(a.qzeros)) & 15) != 0)
@@ -1081,7 +1089,7 @@ cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, 
     while ((1 << p.g_shift) < a.G) ++p.g_shift;
   }
   p.n_tiles = (a.N + kTileN - 1) / kTileN;
-  if (layout == 0 && tcq_applicable(a, acc_ws, tickets)) {
+  if (layout == 0 && gemm_tcq_applicable(a, acc_ws, tickets)) {
     const int BQ = a.M <= 16 ? 16 : (a.M <= 32 ? 32 : (a.M <= 64 ? 64 : 128));
     CUtensorMap tmxq, tmwq;
     p.m_tiles = 1;
@@ -1090,7 +1098,7 @@ cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, 
     p.dbg = (knob(3) == 9 ? 1 : 0) | ((knob(20) & 15) << 1);   // knob 20: timing experiments (results invalid)
     cudaError_t eq = make_x_tmap(a.x, a.ldx, a.M, a.K, BQ, &tmxq);
     if (eq == cudaSuccess)
-      eq = make_tmap_2d(a.qweight, 1, (uint64_t)(a.N / 8), (uint64_t)a.K, (uint64_t)(a.N / 8) * 4, 16, kBK, &tmwq, false);
+      eq = make_tmap_2d(a.qweight, 1, (uint64_t)(a.N / 8), (uint64_t)a.K, (uint64_t)(a.N / 8) * 4, 16, 2 * kBK, &tmwq, false);
     if (eq == cudaSuccess) {
       switch (BQ) {
         case 16: return launch_tcq<16>(tmxq, tmwq, p, st);

@@ -75,6 +75,8 @@ cudaError_t gemv_fast_layout(const FastArgs& a, cudaStream_t st);
 
 // tensor-core path; layout: 0 = GEMM, 1 = GEMV, 2 = FAST (qweight/qzeros reinterpretations documented in gemm_tc.cu)
 cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, cudaStream_t st);
+// true when gemm_tc(layout 0) would run the small-M kernel (TMA-staged packed weights) for these arguments
+bool gemm_tcq_applicable(const GemmArgs& a, const float* acc_ws, const int* tickets);
 cudaError_t gemm_tcq_debug_read(void* dst, size_t bytes);   // phase timestamps of the last small-M launch (knob 3 == 9)
 
 // decode program (program.cu)

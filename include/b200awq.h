@@ -63,7 +63,8 @@ int b200awq_dequantize_gemm(const int32_t* qweight, const void* scales, const in
                             int K, int N, int group_size, b200awq_stream_t stream);
 
 /* Y[M, N] f16 = X[M, K] f16 . deq(W) (+ bias[N] f16 if non-null), GEMM layout.  ldx = row pitch of X in
- * elements (>= K).  M <= 8 runs the CUDA-core GEMV, larger M the tcgen05 tensor-core kernel. */
+ * elements (>= K).  M <= 4 runs the persistent tensor-core GEMV (M <= 8 where the small-M kernel does not apply),
+ * 5 <= M <= 128 the small-M tcgen05 kernel with TMA-staged packed weights, larger M the tcgen05 GEMM. */
 int b200awq_gemm_forward(const void* x, int64_t ldx, const int32_t* qweight, const void* scales,
                          const int32_t* qzeros, const void* bias, void* y, int M, int K, int N, int group_size,
                          void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
@@ -119,7 +120,8 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
 /* Tuning / debug knobs (process-global; used by the micro-benchmarks and layout self-tests).
  *   key 0: GEMV rows per warp override: 32 / 64 / 128 (0 = heuristic)
  *   key 1: tensor-core path split-K override (0 = heuristic)
- *   key 2: M threshold at or below which the CUDA-core GEMV is used (default 8)
+ *   key 2: M threshold at or below which the GEMV kernels are used (default 8; the GEMM-layout entry point lowers it to 4
+ *          wherever the small-M tensor-core kernel of key 19 applies: it is faster from 5 tokens on)
  *   key 3: 1 = the persistent GEMV records per-CTA phase timestamps (read with b200awq_debug_read);
  *          2 = the decode-program kernel records per-op phase timestamps of its first 8 CTAs / 32 ops
  *          (b200awq_debug_read then returns [op][cta][8] uint64 ns: op begin, previous op complete, activations
@@ -155,12 +157,12 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *           after this long; raise it under compute-sanitizer / a debugger, where kernels run orders of magnitude slower
  *   key 15: 1 = wrap every launching entry point in an NVTX range named after it (profiler timelines); default 0
  *   key 19: 1 = never use the small-M kernel with TMA-staged packed weights (gemm_tcq_kernel; default: every GEMM-layout
- *           call with 9 <= M <= 128 (or M above key 2's threshold), G >= 64, N % 128 == 0 runs it)
+ *           call with 5 <= M <= 128 (M above key 2's threshold), G >= 64, K % 128 == 0, N % 128 == 0 runs it)
  *   key 20: small-M kernel timing experiments (outputs are WRONG while set): bit 0 = producers skip the dequantisation and
  *           the shared-memory stores, bit 1 = producers skip the generic->async proxy fence, bit 2 = no MMA is
  *           issued (commits only), bit 3 = one MMA per k-step instead of four
- *   key 21: small-M kernel work cut: 0 = balanced (n-tile, k-step) ranges below 64 tokens, tile-aligned ranges from 64 tokens
- *           (no straddling segments, whole tiles store directly); 1 = always balanced; 2 = always tile-aligned
+ *   key 21: small-M kernel work cut: 0 = tile-aligned ranges when N / 128 <= SM count (or from 64 tokens on), balanced
+ *           (n-tile, k-step pair) ranges otherwise; 1 = always balanced; 2 = tile-aligned whenever possible
  *   key 14: decode program kind (read at b200awq_program_create): 0 = stream variant when the sequence fits it,
  *           else the split-K kernel; 1 = split-K kernel only; 2 = stream variant only
  */
