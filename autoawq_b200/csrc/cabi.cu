@@ -138,6 +138,15 @@ int b200awq_gemm_forward(const void* x, int64_t ldx, const int32_t* qweight, con
   return fold(gemm_tc(a, 0, ws.acc, ws.tickets, st));
 }
 
+int b200awq_tcq_plan(int M, int K, int N, int group_size, int sm_count, int mode, int* grid, int* pairs_per_tile) {
+  const int G = group_size <= 0 ? K : group_size;
+  if (!grid || !pairs_per_tile || sm_count <= 0 || !shape_ok(M, K, N, G)) return B200AWQ_EINVAL;
+  if (!gemm_tcq_shape_ok(M, K, N, G)) return B200AWQ_EUNSUPPORTED;
+  *pairs_per_tile = K / 128;
+  *grid = gemm_tcq_grid(N / 128, K / 128, M, sm_count, mode);
+  return B200AWQ_OK;
+}
+
 int b200awq_gemv_forward(const void* x, int64_t ldx, const int32_t* qweight, const void* scales,
                          const int32_t* qzeros, const void* bias, void* y, int M, int K, int N, int group_size,
                          void* workspace, size_t workspace_bytes, b200awq_stream_t stream) {

@@ -654,6 +654,7 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
       const bool leader = elect_one();
       const uint32_t NW = (uint32_t)p.N >> 3;
       const uint32_t tx = (uint32_t)Cfg::kQTileBytes + (uint32_t)ng * 320u;
+      const int pf_ahead = p.ksplit;   // (field reused by this kernel: L2 prefetch distance in pairs)
       int qs = 0;
       uint32_t qph = 0;
       for (int t = t_begin; t < t_end;) {
@@ -664,6 +665,14 @@ __global__ void __launch_bounds__(TcqCfg<BT>::kThreads, 1)
           uint8_t* dst = q_base + (size_t)qs * Cfg::kQStageBytes;
           const uint32_t g = (uint32_t)(d * Cfg::kQRows) >> p.g_shift;
           if (leader) {
+            // optional HBM -> L2 prefetch of the pair pf_ahead positions further down this CTA's range (knob 22)
+            if (pf_ahead > 0) {
+              const int tp = t + (d - d0) + pf_ahead;
+              if (tp < t_end) {
+                const int ntp = tp / KP;
+                tma_prefetch_l2_2d(&tmq, ntp * 16, (tp - ntp * KP) * Cfg::kQRows);
+              }
+            }
             mbar_arrive_expect_tx(&qfull[qs], tx);
             tma_load_2d(dst, &tmq, &qfull[qs], nt * 16, d * Cfg::kQRows);
             for (int h = 0; h < ng; ++h) {
@@ -1005,6 +1014,37 @@ static cudaError_t dispatch_bt(int BT, const CUtensorMap& tm, const CUtensorMap&
   }
 }
 
+// Grid of the small-M kernel = how the linearised (n-tile, k-step pair) sequence is cut (CTA b owns the pairs
+// [T b / grid, T (b + 1) / grid), T = n_tiles * KP).  mode = knob 21.
+int gemm_tcq_grid(int n_tiles, int KP, int M, int sms, int mode) {
+  const long long T = (long long)n_tiles * KP;
+  long long grid = T / 2;   // balanced ranges: every CTA streams the same bytes; at least 2 pairs per CTA
+  if (grid < 1) grid = 1;
+  if (grid > sms) grid = sms;
+  // Tile-aligned ranges (knob 21: 1 = never, 2 = always): a range that never straddles an n-tile has ONE segment, and a
+  // range that is a whole tile stores fp16 directly - no fp32 REDs, no ticket, no read-back (M * 128 REDs per segment,
+  // M / 16 L2 round trips per finalised tile).
+  if (mode != 1) {
+    long long g = 0;
+    if (n_tiles <= sms) {
+      // every tile is cut into ks ranges (boundaries b * KP / ks never cross a tile since the grid is a multiple of
+      // n_tiles); ks = 1 stores whole tiles directly.  Measured better than the balanced cut at every M <= 128 on the
+      // shapes with N / 128 <= 148 (profiles/r02_tcq_sweep.json).
+      int ks = sms / n_tiles;
+      if (ks > KP / 2) ks = KP / 2;
+      if (ks < 1) ks = 1;
+      g = (long long)n_tiles * ks;
+    } else if (mode == 2 || M >= 64) {
+      // more tiles than SMs: whole tiles per CTA when they divide evenly (224 tiles -> 112 CTAs x 2); below 64 tokens
+      // the balanced cut wins there (all 148 SMs stream, the split-K traffic is small)
+      const int tpc = (n_tiles + sms - 1) / sms;
+      if (n_tiles % tpc == 0) g = n_tiles / tpc;
+    }
+    if (g > 0) grid = g;
+  }
+  return (int)grid;
+}
+
 template <int BT>
 static cudaError_t launch_tcq(const CUtensorMap& tm, const CUtensorMap& tmq, const TcParams& p, cudaStream_t st) {
   using Cfg = TcqCfg<BT>;
@@ -1017,42 +1057,19 @@ static cudaError_t launch_tcq(const CUtensorMap& tm, const CUtensorMap& tmq, con
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  const int KP = p.K / Cfg::kQRows, sms = sm_count();   // work unit: a pair of k-steps
-  const long long T = (long long)p.n_tiles * KP;
-  long long grid = T / 2;   // balanced ranges: every CTA streams the same bytes; at least 2 pairs per CTA
-  if (grid < 1) grid = 1;
-  if (grid > sms) grid = sms;
-  // Tile-aligned ranges (knob 21: 1 = never, 2 = always): a range that never straddles an n-tile has ONE segment, and a
-  // range that is a whole tile stores fp16 directly - no fp32 REDs, no ticket, no read-back (M * 128 REDs per segment,
-  // M / 16 L2 round trips per finalised tile).
-  const int mode = knob(21);
-  if (mode != 1) {
-    long long g = 0;
-    if (p.n_tiles <= sms) {
-      // every tile is cut into ks ranges (boundaries b * KP / ks never cross a tile since the grid is a multiple of
-      // n_tiles); ks = 1 stores whole tiles directly.  Measured better than the balanced cut at every M <= 128 on the
-      // shapes with N / 128 <= 148 (profiles/r02_tcq_sweep.json).
-      int ks = sms / p.n_tiles;
-      if (ks > KP / 2) ks = KP / 2;
-      if (ks < 1) ks = 1;
-      g = (long long)p.n_tiles * ks;
-    } else if (mode == 2 || p.M >= 64) {
-      // more tiles than SMs: whole tiles per CTA when they divide evenly (224 tiles -> 112 CTAs x 2); below 64 tokens
-      // the balanced cut wins there (all 148 SMs stream, the split-K traffic is small)
-      const int tpc = (p.n_tiles + sms - 1) / sms;
-      if (p.n_tiles % tpc == 0) g = p.n_tiles / tpc;
-    }
-    if (g > 0) grid = g;
-  }
+  const int grid = gemm_tcq_grid(p.n_tiles, p.K / Cfg::kQRows, p.M, sm_count(), knob(21));
   return launch_kernel(kern, dim3((unsigned)grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tm, tmq, p);
 }
 
 // Small-M path (M <= kTcqMaxM, GEMM layout, G >= 64, N % 128 == 0): see gemm_tcq_kernel.  The fp32 split-K scratch is
 // the caller's workspace: M * N floats fit the documented min(M, 64) * N * 8 bytes for every M <= 128.
 constexpr int kTcqMaxM = 128;
+bool gemm_tcq_shape_ok(int M, int K, int N, int G) {
+  return M >= 1 && M <= kTcqMaxM && G >= 64 && (K % 128) == 0 && (N % kTileN) == 0 && N / kTileN <= 4096;
+}
 bool gemm_tcq_applicable(const GemmArgs& a, const float* acc_ws, const int* tickets) {
   if (knob(19) == 1) return false;
-  if (a.M > kTcqMaxM || a.G < 64 || (a.K % 128) != 0 || (a.N % kTileN) != 0 || a.N / kTileN > 4096) return false;
+  if (!gemm_tcq_shape_ok(a.M, a.K, a.N, a.G)) return false;
   if (acc_ws == nullptr || tickets == nullptr) return false;
   if (((reinterpret_cast<uintptr_t>(a.qweight) | reinterpret_cast<uintptr_t>(a.scales) |
         reinterpret_cast<uintptr_t>(a.qzeros)) & 15) != 0)
@@ -1093,7 +1110,7 @@ cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, 
     const int BQ = a.M <= 16 ? 16 : (a.M <= 32 ? 32 : (a.M <= 64 ? 64 : 128));
     CUtensorMap tmxq, tmwq;
     p.m_tiles = 1;
-    p.ksplit = 1;
+    p.ksplit = knob(22);   // small-M kernel: L2 prefetch distance in k-step pairs (0 = off)
     p.has_tmq = 1;
     p.dbg = (knob(3) == 9 ? 1 : 0) | ((knob(20) & 15) << 1);   // knob 20: timing experiments (results invalid)
     cudaError_t eq = make_x_tmap(a.x, a.ldx, a.M, a.K, BQ, &tmxq);

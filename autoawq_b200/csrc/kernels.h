@@ -77,6 +77,8 @@ cudaError_t gemv_fast_layout(const FastArgs& a, cudaStream_t st);
 cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, cudaStream_t st);
 // true when gemm_tc(layout 0) would run the small-M kernel (TMA-staged packed weights) for these arguments
 bool gemm_tcq_applicable(const GemmArgs& a, const float* acc_ws, const int* tickets);
+bool gemm_tcq_shape_ok(int M, int K, int N, int G);                       // the kernel's shape envelope
+int gemm_tcq_grid(int n_tiles, int KP, int M, int sms, int mode);         // its work cut (host logic, CPU-testable)
 cudaError_t gemm_tcq_debug_read(void* dst, size_t bytes);   // phase timestamps of the last small-M launch (knob 3 == 9)
 
 // decode program (program.cu)

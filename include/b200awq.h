@@ -117,6 +117,13 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
                                  int sorted_len, int E, int K, int N, int group_size, int mul_weights, int block_size,
                                  void* workspace, size_t workspace_bytes, b200awq_stream_t stream);
 
+/* Host-side plan of the small-M tensor-core kernel (no GPU needed): for a GEMM-layout call of this shape on a device with
+ * `sm_count` SMs, *grid = number of CTAs and *pairs_per_tile = K / 128; CTA b owns the contiguous range
+ * [T b / grid, T (b + 1) / grid) of the linearised (128-column tile, 128-row pair) sequence, T = (N / 128) * (K / 128).
+ * `mode` as knob 21.  B200AWQ_EUNSUPPORTED when the shape is outside that kernel's envelope
+ * (M <= 128, G >= 64, K % 128 == 0, N % 128 == 0). */
+int b200awq_tcq_plan(int M, int K, int N, int group_size, int sm_count, int mode, int* grid, int* pairs_per_tile);
+
 /* Tuning / debug knobs (process-global; used by the micro-benchmarks and layout self-tests).
  *   key 0: GEMV rows per warp override: 32 / 64 / 128 (0 = heuristic)
  *   key 1: tensor-core path split-K override (0 = heuristic)
@@ -163,6 +170,7 @@ int b200awq_grouped_gemm_forward(const void* x, int x_rows_per_token, const int3
  *           issued (commits only), bit 3 = one MMA per k-step instead of four
  *   key 21: small-M kernel work cut: 0 = tile-aligned ranges when N / 128 <= SM count (or from 64 tokens on), balanced
  *           (n-tile, k-step pair) ranges otherwise; 1 = always balanced; 2 = tile-aligned whenever possible
+ *   key 22: small-M kernel: HBM -> L2 prefetch distance in k-step pairs ahead of the shared-memory ring (0 = off, default)
  *   key 14: decode program kind (read at b200awq_program_create): 0 = stream variant when the sequence fits it,
  *           else the split-K kernel; 1 = split-K kernel only; 2 = stream variant only
  */

@@ -27,6 +27,11 @@ for (K, N) in [(4096, 4096), (4096, 28672), (14336, 4096)]:
             row[name] = round(time_kernel(torch, lambda i: ext.linear_forward("gemm", x, qw[i], sc[i], qz[i], G), nbuf,
                                           iters=100, warm=5), 2)
         ext.set_knob(20, 0)
+        for pf in (8, 16, 32, 64):      # HBM -> L2 prefetch distance in k-step pairs (knob 22)
+            ext.set_knob(22, pf)
+            row[f"l2_prefetch_{pf}"] = round(time_kernel(torch, lambda i: ext.linear_forward("gemm", x, qw[i], sc[i], qz[i], G),
+                                                         nbuf, iters=100, warm=5), 2)
+        ext.set_knob(22, 0)
         out[f"{K}x{N} M={M}"] = row
     del qw, qz, sc
     torch.cuda.empty_cache()
