@@ -14,8 +14,8 @@
 // Pipeline: NS smem stages, one "full" mbarrier per stage (8 producer-warp arrivals + 1 TMA expect_tx),
 // one "empty" mbarrier per stage (tcgen05.commit); two TMEM accumulator buffers with tmem_full /
 // tmem_empty mbarriers, so the epilogue of one tile overlaps the main loop of the next.
-// Persistent CTAs walk (n_tile, m_tile, k_split) work items.  Split-K (only for M <= 64, where the
-// problem is HBM-bound and 148 SMs must all stream weights) reduces through fp32 atomics into the
+// Persistent CTAs walk (n_tile, m_tile, k_split) work items.  Split-K (only for M <= 256 and fewer tiles than SMs, where
+// the problem is HBM-bound and 148 SMs must all stream weights) reduces through fp32 atomics into the
 // caller's zeroed workspace; the last CTA of a tile rounds to fp16 and restores the zeros.
 #include <cuda.h>
 
@@ -428,13 +428,22 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
         if (last) {
           __threadfence();
           if (n_ok) {
-            for (int j = 0; j < BT; ++j) {
-              const int m = m0 + j;
-              if (m >= p.M) break;
-              float* a = &p.acc_ws[(int64_t)m * p.N + n];
-              const float f = ldcg_f1(a);
-              *a = 0.f;
-              p.y[(int64_t)m * p.N + n] = __float2half_rn(f + bias_v);
+            // 16 tokens per L2 round trip (loads first, then the stores): one token at a time cost ~0.45 us each
+            for (int j0 = 0; j0 < BT && m0 + j0 < p.M; j0 += 16) {
+              float f[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int m = m0 + j0 + j;
+                f[j] = m < p.M ? ld_relaxed_f32(&p.acc_ws[(int64_t)m * p.N + n]) : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int m = m0 + j0 + j;
+                if (m < p.M) {
+                  p.acc_ws[(int64_t)m * p.N + n] = 0.f;
+                  p.y[(int64_t)m * p.N + n] = __float2half_rn(f[j] + bias_v);
+                }
+              }
             }
           }
           if (et == 0) p.tickets[nt * p.m_tiles + mt] = 0;
@@ -1062,7 +1071,7 @@ static cudaError_t launch_tcq(const CUtensorMap& tm, const CUtensorMap& tmq, con
 }
 
 // Small-M path (M <= kTcqMaxM, GEMM layout, G >= 64, N % 128 == 0): see gemm_tcq_kernel.  The fp32 split-K scratch is
-// the caller's workspace: M * N floats fit the documented min(M, 64) * N * 8 bytes for every M <= 128.
+// the caller's workspace: M * N floats fit the documented min(M, 128) * N * 8 bytes.
 constexpr int kTcqMaxM = 128;
 bool gemm_tcq_shape_ok(int M, int K, int N, int G) {
   return M >= 1 && M <= kTcqMaxM && G >= 64 && (K % 128) == 0 && (N % kTileN) == 0 && N / kTileN <= 4096;
@@ -1130,13 +1139,14 @@ cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, 
   const int KS = a.K / kBK;
   int ksplit = 1;
   const int tiles = p.n_tiles * p.m_tiles;
-  if (a.M <= kMaxSplitM && acc_ws != nullptr && tickets != nullptr && tiles < sm_count() && tiles <= 4096) {
+  // fp32 partial sums: the workspace holds min(M, kMaxSplitM) * N 8-byte words = room for 2 * kMaxSplitM token rows
+  if (a.M <= 2 * kMaxSplitM && acc_ws != nullptr && tickets != nullptr && tiles < sm_count() && tiles <= 4096) {
     ksplit = sm_count() / tiles;
     if (ksplit < 1) ksplit = 1;
     while (ksplit > 1 && KS / ksplit < 4) --ksplit;  // at least 4 k-steps per slice
   }
   const int forced = knob(1);
-  if (forced > 0 && a.M <= kMaxSplitM && acc_ws != nullptr && tickets != nullptr) ksplit = forced > KS ? KS : forced;
+  if (forced > 0 && a.M <= 2 * kMaxSplitM && acc_ws != nullptr && tickets != nullptr) ksplit = forced > KS ? KS : forced;
   p.ksplit = ksplit;
   CUtensorMap tm, tmq;
   cudaError_t e = make_x_tmap(a.x, a.ldx, a.M, a.K, BT, &tm);

@@ -33,7 +33,7 @@ struct FastArgs {
 
 // workspace carve-up (see b200awq_workspace_bytes): tickets first, fp32 accumulators after
 constexpr size_t kTicketBytes = 16384;  // 4096 int tickets
-constexpr int kMaxSplitM = 64;          // rows of fp32 scratch kept for split-K
+constexpr int kMaxSplitM = 128;         // rows of 8-byte scratch kept for split-K (= 256 rows of fp32 partial sums)
 
 // knobs (cabi.cu)
 int knob(int key);

@@ -129,7 +129,7 @@ def linear_forward(layout: str, x, qweight, scales, qzeros, group_size: int, bia
     """Y = X . deq(W) (+ bias) for layout in {"gemm", "gemv", "fast"}; returns [M, N] fp16 (written into `out`
     when given: a contiguous [M, N] fp16 tensor).  The hot call of an eager decode loop (160 per token): weights are
     validated once per tensor, no context-manager object, no extra ABI call (b200awq_workspace_bytes is
-    16384 + min(M, 64) * N * 8, restated here)."""
+    16384 + min(M, 128) * N * 8, restated here)."""
     try:
         fn = _LAYOUT[layout][0]
     except KeyError:
@@ -156,7 +156,7 @@ def linear_forward(layout: str, x, qweight, scales, qzeros, group_size: int, bia
         torch.cuda.set_device(di)
     try:
         st = _raw_stream(di) if _raw_stream is not None else torch.cuda.current_stream(dev).cuda_stream
-        need = _WS_TICKETS + (M if M < 64 else 64) * N * 8
+        need = _WS_TICKETS + (M if M < 128 else 128) * N * 8
         ws = _WS.get((di, st))
         if ws is None or ws.numel() < need:
             ws = _workspace(dev, st, need)

@@ -52,8 +52,9 @@ const char* b200awq_error_string(int code);
 /* last CUDA error text seen by this library on the calling thread ("" if none) */
 const char* b200awq_last_cuda_error(void);
 
-/* Bytes of scratch the forward entry points may need for (M, K, N): 16 KB of tickets + min(M, 64) * N 64-bit words
- * (split-K partials: packed fixed-point sum + tile count per element for the M <= 8 GEMV, fp32 pairs otherwise).
+/* Bytes of scratch the forward entry points may need for (M, K, N): 16 KB of tickets + min(M, 128) * N 64-bit words
+ * (split-K partials: packed fixed-point sum + tile count per element for the M <= 8 GEMV, fp32 sums of up to 256 token
+ * rows otherwise).
  * The caller allocates once (zero-initialised!) and passes it to every call; the library restores the
  * all-zero ticket state before each kernel exits, so one buffer serves any number of calls on one stream. */
 size_t b200awq_workspace_bytes(int M, int K, int N);

@@ -190,6 +190,10 @@ def test_workspace_is_self_cleaning(ext):
     y0 = e.linear_forward("gemm", *args)
     x16 = np.random.default_rng(2).standard_normal((24, 4096)).astype(np.float16)
     e.linear_forward("gemm", _t(x16), *args[1:])
+    x200 = np.random.default_rng(3).standard_normal((200, 4096)).astype(np.float16)   # split-K of the tcgen05 GEMM (M <= 256)
+    w = O.dequantize_gemm(c["qweight"], c["qzeros"], c["scales"], 128)
+    y200 = e.linear_forward("gemm", _t(x200), *args[1:]).cpu().numpy()
+    _close(y200, O.gemm_f64(x200, w), _budget(x200, w), WR_TC, "split-K tcgen05 GEMM, M = 200")
     torch.cuda.synchronize()
     for ws in e._WS.values():
         assert int(ws.view(torch.int32).ne(0).sum()) == 0

@@ -121,7 +121,7 @@ def test_cabi_exports_every_declared_symbol(built):
     assert _cabi.lib.b200awq_abi_version() == 1
     assert _cabi.lib.b200awq_error_string(3).decode().startswith("workspace")
     assert _cabi.lib.b200awq_workspace_bytes(1, 4096, 4096) == 16384 + 4096 * 8   # tickets + one 64-bit word per element
-    assert _cabi.lib.b200awq_workspace_bytes(4096, 4096, 4096) == 16384 + 64 * 4096 * 8
+    assert _cabi.lib.b200awq_workspace_bytes(4096, 4096, 4096) == 16384 + 128 * 4096 * 8
 
 
 def test_cabi_argument_validation_without_gpu(built):
@@ -265,9 +265,9 @@ def test_python_workspace_size_restates_the_abi(built):
     from autoawq_b200 import ext
     from autoawq_b200._cabi import lib
 
-    for M in (1, 8, 63, 64, 65, 4096):
+    for M in (1, 8, 63, 64, 65, 127, 128, 129, 256, 4096):
         for N in (8, 4096, 28672):
-            assert lib.b200awq_workspace_bytes(M, 4096, N) == ext._WS_TICKETS + min(M, 64) * N * 8
+            assert lib.b200awq_workspace_bytes(M, 4096, N) == ext._WS_TICKETS + min(M, 128) * N * 8
 
 
 def test_comm_and_stream_argument_validation_without_gpu(built):
