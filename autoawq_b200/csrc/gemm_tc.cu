@@ -1145,6 +1145,10 @@ cudaError_t gemm_tc(const GemmArgs& a, int layout, float* acc_ws, int* tickets, 
     if (ksplit < 1) ksplit = 1;
     while (ksplit > 1 && KS / ksplit < 4) --ksplit;  // at least 4 k-steps per slice
   }
+  // Above 64 tokens the reduction is no longer free: ~0.15 us per token (M * 128 fp32 REDs per CTA, M / 16 L2 round trips
+  // for the finaliser) against ~0.5 us per k-step saved on the critical path (profiles/r02_m_sweep_final.json: 14336 x
+  // 4096 at M = 256 114 -> 66 us with 4 slices, 4096 x 4096 45 -> 47 us) - split only when it pays.
+  if (a.M > 64 && ksplit > 1 && (float)(KS - KS / ksplit) * 0.5f < 0.15f * (float)a.M) ksplit = 1;
   const int forced = knob(1);
   if (forced > 0 && a.M <= 2 * kMaxSplitM && acc_ws != nullptr && tickets != nullptr) ksplit = forced > KS ? KS : forced;
   p.ksplit = ksplit;

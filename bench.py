@@ -352,6 +352,41 @@ def gemv_4096_leg(torch, ext, dev, steps, peaks):
             "pool": f"{pool} distinct weight sets ({pool * b / 1e6:.0f} MB > L2), one CUDA graph of {pool} launches"}
 
 
+def small_batch_leg(torch, ext, dev, steps, peaks):
+    """Batched decode (BASELINE config 3's small-M end): one linear at M = 8 / 16 / 64 tokens on
+    4096 x 4096 and 4096 x 28672 (gate|up), stand-alone launches rotating over > L2 of distinct weights, CUDA graph, CUDA
+    events.  HBM-bound up to M ~ 73: the figure of merit is the fraction of the HBM peak."""
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(321)
+    for (K, N) in ((HIDDEN, HIDDEN), (HIDDEN, 2 * INTER)):
+        wb = K * N // 2
+        pool = max(3, int(400e6 // wb) + 1)
+        ws = []
+        for _ in range(pool):
+            qw = torch.randint(-2**31, 2**31 - 1, (K, N // 8), dtype=torch.int32, device=dev, generator=g)
+            qz = torch.randint(-2**31, 2**31 - 1, (K // GROUP, N // 8), dtype=torch.int32, device=dev, generator=g)
+            s = ((torch.rand((K // GROUP, N), device=dev, generator=g) * 0.5 + 0.75) / (6.1 * K**0.5)).half()
+            ws.append((qw, s, qz))
+        for M in (8, 16, 64):
+            x = torch.randn((M, K), device=dev, dtype=torch.float16, generator=g)
+
+            def sweep():
+                for w in ws:
+                    ext.gemm_forward_cuda(x, w[0], w[1], w[2], 8)
+
+            gr, _ = capture(torch, sweep)
+            n = max(5, steps)
+            sec = timed(torch, gr.replay, n, 3)
+            us = sec / n / pool * 1e6
+            bts = linear_bytes(K, N, M)
+            out[f"{K}x{N} M={M}"] = {"us": round(us, 2), "gbs": round(bts / us / 1e3, 1),
+                                     "frac_hbm": round(bts / us / 1e3 / peaks["hbm_gbs"], 4),
+                                     "tflops": round(2.0 * M * K * N / us / 1e6, 1)}
+        del ws
+    out["kernel"] = "gemm_tcq_kernel (tcgen05, TMA-staged packed weights), 5 <= M <= 128"
+    return out
+
+
 def prefill_leg(torch, rep_weights, dev, steps, peaks):
     """BASELINE config 3 as a secondary leg of the default run: bs=1, seq=4096 through every quantised linear
     (tcgen05 kernel), same weights; tok/s, TFLOP/s, fraction of the sustained bf16 peak."""
@@ -831,6 +866,7 @@ def main():
         config["triton_reference"] = triton_reference_leg(torch, rep, M, max(5, a.steps // 2), 3)
         if a.mode == "decode":
             config["gemv_4096"] = gemv_4096_leg(torch, rep.ext, dev, a.steps, peaks)
+            config["small_batch"] = small_batch_leg(torch, rep.ext, dev, a.steps, peaks)
             eager_ops = timed(torch, lambda: rep.step(rep.h), max(3, a.steps // 5), 2)
             config["per_op_eager_tok_s"] = round(max(3, a.steps // 5) / eager_ops, 1)
             config["prefill"] = prefill_leg(torch, rep.w, dev, a.steps, peaks)
