@@ -703,7 +703,9 @@ def main():
                                            f"torch.matmul fp16, M={m_eff}), x32 extrapolated; thread count "
                                            f"auto-picked from a sweep (fastest)"},
                 "e2e": {"value": val, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+                "gpu_launches": 0,
+                # the CPU path takes ~15 s per sampled layer at M = 1: the run stops after 150 s of samples and says so
+                "steps_requested": a.steps, "steps_truncated": len(per_layer) < a.steps}
         print(json.dumps(line), flush=True)
         return
 
