@@ -536,7 +536,8 @@ __global__ void __launch_bounds__(tc_threads<LAYOUT>(), 1)
 //     224 tiles on 148 SMs two waves deep).  A range crosses at most a few n-tiles = segments; a segment that holds a
 //     whole K column stores fp16 directly, a partial one adds fp32 into the caller's zeroed workspace and bumps the
 //     tile's ticket by its number of k-step pairs; the contributor that completes K rounds, adds the bias, restores
-//     zeros.  From 64 tokens on the ranges are tile-aligned instead (launch_tcq).
+//     zeros.  Wherever N / 128 <= SM count (and from 64 tokens on) the ranges are tile-aligned instead: gemm_tcq_grid.
+//   * knob 22 = optional HBM -> L2 prefetch ahead of the ring: measured, no gain (profiles/r02_tcq_knob20.json).
 template <int BT>
 struct TcqCfg {
   static constexpr int kNS = 4;                                            // A stages (producers -> MMA), 2 per team
