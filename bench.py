@@ -58,8 +58,43 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.nv_rows, self.nv_stop, self.nv_thread, self.nv_max = None, [], False, None, None
+
+    # NVML (pynvml / nvidia-ml-py) polled every ~2 ms from a thread: a decode run's timed region is ~40 ms, shorter than
+    # nvidia-smi's first sample (its -lms loop delivered 0-2 rows there); nvidia-smi stays as the fallback.
+    def _nvml_start(self):
+        import pynvml as nv
+
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.index
+        if vis and all(t.strip().isdigit() for t in vis.split(",")):
+            idx = int(vis.split(",")[self.index])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        self.nv_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+
+        def loop():
+            while not self.nv_stop:
+                try:
+                    mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = int(get_reasons(h))
+                    self.nv_rows.append((time.time(), mhz, [n for n, b in bits.items() if r & b]))
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.002)
+
+        self.nvml = nv
+        self.nv_thread = threading.Thread(target=loop, daemon=True)
+        self.nv_thread.start()
 
     def start(self):
+        try:
+            self._nvml_start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
@@ -73,6 +108,13 @@ class ClockSampler:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            self.nv_stop = True
+            self.nv_thread.join(timeout=1.0)
+            sm = sorted(m for ts, m, _ in self.nv_rows if t0 <= ts <= t1)
+            reasons = sorted({n for ts, _, rs in self.nv_rows if t0 <= ts <= t1 for n in rs})
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.nv_max, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, 2 ms period, samples inside the timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -632,6 +674,15 @@ def mixtral_leg(torch, dev, steps, layers=32):
     gr, _ = capture(torch, step)
     n = max(5, steps // 2)
     sec = timed(torch, gr.replay, n, 3)
+    # the routing is data-dependent: a step whose activations went non-finite would route nowhere and "run" in no time.
+    # Check the replayed step's own output and routing state (2 distinct experts in the last layer, finite output).
+    h_chk = step()
+    torch.cuda.synchronize()
+    finite = bool(torch.isfinite(h_chk).all().item())
+    experts_last = sorted(int(v) for v in tid.flatten().tolist())
+    rms = float(h_chk.float().pow(2).mean().sqrt().item()) if finite else float("nan")
+    if not finite or len(set(experts_last)) != topk or not all(0 <= e < E for e in experts_last):
+        raise RuntimeError(f"mixtral leg: invalid step (finite={finite}, experts of the last layer={experts_last})")
     wb = lambda K, N: K * N // 2 + (K // GROUP) * N * 2 + (K // GROUP) * N // 2  # noqa: E731
     active = layers * (wb(H, QKV) + wb(H, H) + topk * (wb(H, 2 * I) + wb(I, H)))
     total = layers * (wb(H, QKV) + wb(H, H) + E * (wb(H, 2 * I) + wb(I, H)))
@@ -642,6 +693,7 @@ def mixtral_leg(torch, dev, steps, layers=32):
             "weights_gb": round(total / 1e9, 2), "gbs_over_active_bytes": round(active / t / 1e9, 1),
             "frac_of_hbm_peak": round(active / t / 1e9 / measured_peaks()["hbm_gbs"], 4),
             "launches_per_step": layers * 13, "cuda_graph": True,
+            "checked": {"output_finite": finite, "output_rms": round(rms, 4), "experts_last_layer": experts_last},
             "multi_gpu": "fits one B200 (24 GB): 2 GPUs = 2 replicas, as for Llama-3-8B"}
 
 
