@@ -346,6 +346,13 @@ __global__ void __launch_bounds__(kV3Threads, 1)
   __shared__ int s_slot[8];       // MOE: output row of each of the job's slots (-1 = padding)
   int row_off = 0;                // MOE: first row of the job's expert in the stacked tensor
   if (MOE) {
+    // The routing tables (num_post_pad, sorted_ids, expert_ids) are the PREDECESSOR's output (moe_align): under
+    // programmatic dependent launch this kernel may start before that kernel has finished, so nothing of them may be read
+    // before the wait - not even to decide that the job is padding (a CTA that exits without waiting would also let the
+    // grid "complete" early and break the chain for the successor).  The expert's weights depend on the routing, so
+    // unlike the dense GEMV there is nothing to prefetch ahead of the wait.  (Found by bench.py's Mixtral leg: with
+    // knob 4 the step ran in 1.8 ms instead of 3.3 ms - jobs saw stale tables and returned as padding.)
+    pdl_wait();
     const int job = blockIdx.y;
     if (job * 8 >= *moe.num_post_pad) return;
     if (threadIdx.x < 8) {

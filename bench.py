@@ -671,18 +671,30 @@ def mixtral_leg(torch, dev, steps, layers=32):
             h = torch.sum(out, dim=1)
         return h
 
-    gr, _ = capture(torch, step)
+    # Reference of the same step WITHOUT programmatic dependent launch (plain stream order), for the validity check below
+    from autoawq_b200 import ext as _ext
+
+    pdl_was = _ext.get_knob(4)
+    _ext.set_knob(4, 0)
+    h_ref = step().clone()
+    torch.cuda.synchronize()
+    experts_ref = sorted(int(v) for v in tid.flatten().tolist())
+    _ext.set_knob(4, pdl_was)
+    gr, h_graph = capture(torch, step)
     n = max(5, steps // 2)
     sec = timed(torch, gr.replay, n, 3)
-    # the routing is data-dependent: a step whose activations went non-finite would route nowhere and "run" in no time.
-    # Check the replayed step's own output and routing state (2 distinct experts in the last layer, finite output).
-    h_chk = step()
+    # The routing is data-dependent: a step that read stale routing tables (a launch-overlap race) or whose activations
+    # went non-finite routes elsewhere or nowhere and "runs" in no time.  The timed graph's own output must be finite,
+    # route two distinct experts in the last layer and agree with the plain-stream-order reference.
     torch.cuda.synchronize()
-    finite = bool(torch.isfinite(h_chk).all().item())
+    finite = bool(torch.isfinite(h_graph).all().item())
     experts_last = sorted(int(v) for v in tid.flatten().tolist())
-    rms = float(h_chk.float().pow(2).mean().sqrt().item()) if finite else float("nan")
-    if not finite or len(set(experts_last)) != topk or not all(0 <= e < E for e in experts_last):
-        raise RuntimeError(f"mixtral leg: invalid step (finite={finite}, experts of the last layer={experts_last})")
+    rms = float(h_graph.float().pow(2).mean().sqrt().item()) if finite else float("nan")
+    max_diff = float((h_graph.float() - h_ref.float()).abs().max().item()) if finite else float("inf")
+    if (not finite or len(set(experts_last)) != topk or not all(0 <= e < E for e in experts_last)
+            or experts_last != experts_ref or max_diff > 0.1 * max(rms, 1e-3) + 0.05):
+        raise RuntimeError(f"mixtral leg: invalid step (finite={finite}, experts of the last layer={experts_last} vs "
+                           f"{experts_ref} without PDL, max |diff| {max_diff:.4f}, rms {rms:.4f})")
     wb = lambda K, N: K * N // 2 + (K // GROUP) * N * 2 + (K // GROUP) * N // 2  # noqa: E731
     active = layers * (wb(H, QKV) + wb(H, H) + topk * (wb(H, 2 * I) + wb(I, H)))
     total = layers * (wb(H, QKV) + wb(H, H) + E * (wb(H, 2 * I) + wb(I, H)))
@@ -693,7 +705,8 @@ def mixtral_leg(torch, dev, steps, layers=32):
             "weights_gb": round(total / 1e9, 2), "gbs_over_active_bytes": round(active / t / 1e9, 1),
             "frac_of_hbm_peak": round(active / t / 1e9 / measured_peaks()["hbm_gbs"], 4),
             "launches_per_step": layers * 13, "cuda_graph": True,
-            "checked": {"output_finite": finite, "output_rms": round(rms, 4), "experts_last_layer": experts_last},
+            "checked": {"output_finite": finite, "output_rms": round(rms, 4), "experts_last_layer": experts_last,
+                        "max_abs_diff_vs_no_pdl_reference": round(max_diff, 5)},
             "multi_gpu": "fits one B200 (24 GB): 2 GPUs = 2 replicas, as for Llama-3-8B"}
 
 
