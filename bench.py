@@ -671,30 +671,48 @@ def mixtral_leg(torch, dev, steps, layers=32):
             h = torch.sum(out, dim=1)
         return h
 
-    # Reference of the same step WITHOUT programmatic dependent launch (plain stream order), for the validity check below
     from autoawq_b200 import ext as _ext
 
-    pdl_was = _ext.get_knob(4)
-    _ext.set_knob(4, 0)
-    h_ref = step().clone()
-    torch.cuda.synchronize()
-    experts_ref = sorted(int(v) for v in tid.flatten().tolist())
-    _ext.set_knob(4, pdl_was)
     gr, h_graph = capture(torch, step)
     n = max(5, steps // 2)
     sec = timed(torch, gr.replay, n, 3)
-    # The routing is data-dependent: a step that read stale routing tables (a launch-overlap race) or whose activations
-    # went non-finite routes elsewhere or nowhere and "runs" in no time.  The timed graph's own output must be finite,
-    # route two distinct experts in the last layer and agree with the plain-stream-order reference.
     torch.cuda.synchronize()
+    # Validity of the TIMED configuration (graph, PDL as set).  The routing is data-dependent and the step is chaotic in
+    # its rounding noise (fp32 split-K order can flip a near-tie in some layer), so two runs cannot be compared end to
+    # end; but every layer must be consistent with ITS OWN inputs.  The last layer's state is still in the static buffers
+    # after a replay: recompute its routing and its MoE output from them with plain torch on OUR dequantised weights.
+    # (A launch-overlap race - a grouped GEMV reading the routing tables before its predecessor finished - made this
+    # leg run "too fast" once: that is what this catches.)
+    wl = ws[-1]
+    logits_l = torch.matmul(xn, wl["router"]).float()
+    probs = torch.softmax(logits_l, dim=-1)
+    want_e = sorted(int(v) for v in torch.topk(probs, topk, dim=-1).indices.flatten().tolist())
+    got_e = [int(v) for v in tid.flatten().tolist()]
+    tw_ok = bool(torch.allclose(tw.flatten(), probs[0, got_e] if all(0 <= v < E for v in got_e) else tw.flatten() + 1,
+                                atol=2e-3))
+    h_ref = torch.zeros((1, H), dtype=torch.float32, device=dev)
+    if sorted(got_e) == want_e:
+        for k, ex in enumerate(got_e):
+            w13 = awq_ext.dequantize_weights_cuda(wl["w13"][0][ex], wl["w13"][1][ex], wl["w13"][2][ex], 0, 0, 0, False)
+            w2 = awq_ext.dequantize_weights_cuda(wl["w2"][0][ex], wl["w2"][1][ex], wl["w2"][2][ex], 0, 0, 0, False)
+            gu_k = torch.matmul(xn.float(), w13.float())
+            a_k = (torch.nn.functional.silu(gu_k[:, :I]) * gu_k[:, I:]).half().float()
+            h_ref += tw[0, k] * torch.matmul(a_k, w2.float()).half().float()
+            del w13, w2
     finite = bool(torch.isfinite(h_graph).all().item())
-    experts_last = sorted(int(v) for v in tid.flatten().tolist())
     rms = float(h_graph.float().pow(2).mean().sqrt().item()) if finite else float("nan")
-    max_diff = float((h_graph.float() - h_ref.float()).abs().max().item()) if finite else float("inf")
-    if (not finite or len(set(experts_last)) != topk or not all(0 <= e < E for e in experts_last)
-            or experts_last != experts_ref or max_diff > 0.1 * max(rms, 1e-3) + 0.05):
-        raise RuntimeError(f"mixtral leg: invalid step (finite={finite}, experts of the last layer={experts_last} vs "
-                           f"{experts_ref} without PDL, max |diff| {max_diff:.4f}, rms {rms:.4f})")
+    max_diff = float((h_graph.float() - h_ref).abs().max().item()) if finite else float("inf")
+    if not finite or sorted(got_e) != want_e or not tw_ok or max_diff > 0.03 * max(rms, 1e-3) + 0.02:
+        raise RuntimeError(f"mixtral leg: the timed step is not consistent with its own inputs (finite={finite}, last "
+                           f"layer routed {got_e}, its logits say {want_e}, routing weights ok={tw_ok}, MoE output max "
+                           f"|diff| vs torch {max_diff:.4f}, rms {rms:.4f})")
+    # the same step without programmatic dependent launch, for the record (PDL hides the launch gaps of 416 small launches)
+    pdl_was = _ext.get_knob(4)
+    _ext.set_knob(4, 0)
+    gr0, _ = capture(torch, step)
+    sec0 = timed(torch, gr0.replay, n, 3)
+    _ext.set_knob(4, pdl_was)
+    experts_last = sorted(got_e)
     wb = lambda K, N: K * N // 2 + (K // GROUP) * N * 2 + (K // GROUP) * N // 2  # noqa: E731
     active = layers * (wb(H, QKV) + wb(H, H) + topk * (wb(H, 2 * I) + wb(I, H)))
     total = layers * (wb(H, QKV) + wb(H, H) + E * (wb(H, 2 * I) + wb(I, H)))
@@ -705,8 +723,10 @@ def mixtral_leg(torch, dev, steps, layers=32):
             "weights_gb": round(total / 1e9, 2), "gbs_over_active_bytes": round(active / t / 1e9, 1),
             "frac_of_hbm_peak": round(active / t / 1e9 / measured_peaks()["hbm_gbs"], 4),
             "launches_per_step": layers * 13, "cuda_graph": True,
+            "ms_per_step_without_pdl": round(sec0 / n * 1e3, 4),
             "checked": {"output_finite": finite, "output_rms": round(rms, 4), "experts_last_layer": experts_last,
-                        "max_abs_diff_vs_no_pdl_reference": round(max_diff, 5)},
+                        "last_layer_routing_matches_its_logits": True,
+                        "last_layer_moe_max_abs_diff_vs_torch": round(max_diff, 5)},
             "multi_gpu": "fits one B200 (24 GB): 2 GPUs = 2 replicas, as for Llama-3-8B"}
 
 
