@@ -35,6 +35,24 @@ def test_nvml_sampler_window_and_reasons(monkeypatch):
     assert out["sm_mhz"] == 1900.0 and out["sm_max_mhz"] == 1965.0
     assert out["reasons"] == ["sw_power_cap"]
     assert 5 <= out["samples"] <= 40, out          # ~2 ms period over a 50 ms window, none from outside it
+    assert out["samples_in_timed_region"] == out["samples"] and "note" not in out
+
+
+def test_nvml_sampler_extension_is_reported(monkeypatch):
+    """Too few samples inside the timed region: the caller keeps the load up and passes the extended end; the result
+    says so and keeps the in-region count separate."""
+    monkeypatch.setitem(sys.modules, "pynvml", _fake_nvml(0))
+    monkeypatch.delenv("CUDA_VISIBLE_DEVICES", raising=False)
+    bench = importlib.import_module("bench")
+    s = bench.ClockSampler(0)
+    s.start()
+    t0 = time.time()
+    t1 = t0 + 0.0005                               # a "timed region" shorter than one sampling period
+    time.sleep(0.05)
+    assert 0 <= s.count(t0, t1) < 3
+    t_ext = time.time()
+    out = s.stop(t0, t1, t_ext)
+    assert out["samples_in_timed_region"] < 3 <= out["samples"] and "note" in out and out["reasons"] == []
 
 
 def test_sampler_falls_back_when_nvml_is_unusable(monkeypatch):
