@@ -895,6 +895,32 @@ def main():
         dist.barrier()
     value = world * tokens_per_step * a.steps / sec
 
+    # What the timed graph computed, against the same step run eagerly through the per-op kernels in plain stream order
+    # (no graph, no PDL): a timed region that skipped work or raced would not reproduce it.  The dense step is not
+    # chaotic (no data-dependent routing; RMSNorm every block), so the comparison holds end to end over the 32 layers.
+    if rank == 0 and a.mode == "decode":
+        try:
+            torch.cuda.synchronize()
+            y_timed = out_static.float().clone()
+            pdl_was = rep.ext.get_knob(4)
+            rep.ext.set_knob(4, 0)
+            try:
+                y_ref = rep.step(rep.h).float().clone()
+                torch.cuda.synchronize()
+            finally:
+                rep.ext.set_knob(4, pdl_was)
+            g_ops.replay()
+            torch.cuda.synchronize()
+            y_ops = out_ops.float()
+            rms = float(y_ref.pow(2).mean().sqrt().item())
+            config["output_check"] = {
+                "finite": bool(torch.isfinite(y_timed).all().item()), "output_rms": round(rms, 4),
+                "timed_step_vs_eager_per_op_max_abs_diff": round(float((y_timed - y_ref).abs().max().item()), 6),
+                "per_op_graph_with_pdl_vs_eager_max_abs_diff": round(float((y_ops - y_ref).abs().max().item()), 6),
+                "how": "last replay of the timed graph vs rep.step() eager with knob 4 = 0, same resident input"}
+        except Exception as ex:  # noqa: BLE001  (a check must never take the bench line down)
+            config["output_check"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+
     # roofline leg: the quantised-linear kernels alone, same weights
     g_lin, _ = capture(torch, lambda: rep.gemm_only(rep.h))
     sec_lin = timed(torch, g_lin.replay, a.steps, a.warmup, dist)
