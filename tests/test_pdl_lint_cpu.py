@@ -14,8 +14,19 @@ EXEMPT = {"stream_pack_kernel", "oneshot_allreduce_kernel", "ll_allreduce_kernel
 def _kernels(path):
     src = open(path).read()
     out = {}
-    for m in re.finditer(r"__global__\s+void(?:\s+__launch_bounds__\([^)]*\))?\s+(\w+)\s*\(", src):
-        name, i = m.group(1), src.index("{", m.end())
+    for m in re.finditer(r"__global__\s+void\s+", src):
+        p = m.end()
+        if src.startswith("__launch_bounds__", p):       # skip the (possibly nested) argument list
+            p = src.index("(", p)
+            depth = 1
+            p += 1
+            while depth:
+                depth += {"(": 1, ")": -1}.get(src[p], 0)
+                p += 1
+        nm = re.match(r"\s*(\w+)\s*\(", src[p:])
+        if nm is None:
+            continue
+        name, i = nm.group(1), src.index("{", p + nm.end())
         depth, j = 1, i + 1
         while depth:
             depth += {"{": 1, "}": -1}.get(src[j], 0)
