@@ -921,7 +921,9 @@ def main():
             chk = {"finite": bool(torch.isfinite(y_timed).all().item()), "output_rms": round(rms_y, 4),
                    "last_layer_act_max_abs_diff_vs_torch": round(d_act, 6),
                    "last_layer_output_max_abs_diff_vs_torch": round(d_y, 6),
-                   "last_layer_consistent": bool(d_act <= 0.02 * rms_act + 0.01 and d_y <= 0.02 * rms_y + 0.01),
+                   # fp16 rounding of gate|up (2^-11 relative, |gate|, |up| up to ~5) propagates to ~0.01 on the largest
+                   # activations; work that was skipped or raced would be off by O(1)
+                   "last_layer_consistent": bool(d_act <= 0.03 * rms_act + 0.03 and d_y <= 0.03 * rms_y + 0.03),
                    "how": "after the last timed replay: silu(gate) * up of the stored xn vs the stored act, act . W_down vs "
                           "the step's output, torch fp32 on dequantize_weights_cuda of the last layer's tensors"}
             pdl_was = rep.ext.get_knob(4)
